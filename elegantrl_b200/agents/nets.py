@@ -1,0 +1,93 @@
+"""Actor / critic ``nn.Module`` containers for the on-policy path.
+
+They hold the parameters the CUDA engine works on *in place* (the engine receives raw pointers into these
+storages, see ``AgentPPO._net_desc``) and provide the plain-PyTorch forward the callers of the hot path need:
+the Evaluator calls ``actor(state)`` and pickles the module (reference ``elegantrl/train/evaluator.py:123,
+176-183``), ``run.py:288-293`` ships ``agent.act`` through a Pipe.  Attribute names / state_dict keys follow the
+reference nets (``elegantrl/agents/AgentPPO.py:348-390`` ActorPPO, ``:425-441`` CriticPPO; MLP builder
+``elegantrl/agents/AgentBase.py:345-365``) so checkpoints' ``state_dict`` s are interchangeable.
+
+The torch methods here are NOT the product path: ``AgentPPO`` routes rollout / GAE / update through
+``libb200rl.so`` and raises if it is missing.
+"""
+import math
+
+import torch as th
+from torch import nn
+
+TEN = th.Tensor
+ACTIVATIONS = {"gelu": nn.GELU, "relu": nn.ReLU}
+
+
+def make_mlp(dims, activation: str = "gelu") -> nn.Sequential:
+    """Linear -> act -> ... -> Linear (no activation on the output), as the reference ``build_mlp``."""
+    act_class = ACTIVATIONS[activation]
+    layers = []
+    for d_in, d_out in zip(dims[:-1], dims[1:]):
+        layers += [nn.Linear(d_in, d_out), act_class()]
+    return nn.Sequential(*layers[:-1])
+
+
+def _init_output_layer(layer: nn.Linear, std: float, bias_const: float = 1e-6):
+    nn.init.orthogonal_(layer.weight, std)
+    nn.init.constant_(layer.bias, bias_const)
+
+
+class _StateNormMixin:
+    state_avg: nn.Parameter
+    state_std: nn.Parameter
+
+    def state_norm(self, state: TEN) -> TEN:
+        return (state - self.state_avg) / (self.state_std + 1e-4)
+
+
+class ActorPPO(nn.Module, _StateNormMixin):
+    """Gaussian policy: mean = MLP(state_norm(s)), std = exp(action_std_log) (state independent)."""
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int, activation: str = "gelu"):
+        super().__init__()
+        self.net = make_mlp([state_dim, *net_dims, action_dim], activation)
+        _init_output_layer(self.net[-1], std=0.1)
+        self.action_std_log = nn.Parameter(th.zeros((1, action_dim)), requires_grad=True)
+        self.state_avg = nn.Parameter(th.zeros((state_dim,)), requires_grad=False)
+        self.state_std = nn.Parameter(th.ones((state_dim,)), requires_grad=False)
+        self.activation = activation
+
+    def forward(self, state: TEN) -> TEN:  # deterministic action for evaluation
+        return self.net(self.state_norm(state)).tanh()
+
+    def get_action(self, state: TEN):  # torch statement of what csrc/policy_step does
+        mean = self.net(self.state_norm(state))
+        std = self.action_std_log.exp()
+        action = mean + std * th.randn_like(mean)
+        return action, self._logprob(mean, std, action)
+
+    def get_logprob_entropy(self, state: TEN, action: TEN):
+        mean = self.net(self.state_norm(state))
+        std = self.action_std_log.exp()
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + std.log()).expand_as(mean).sum(1)
+        return self._logprob(mean, std, action), entropy
+
+    @staticmethod
+    def _logprob(mean: TEN, std: TEN, action: TEN) -> TEN:
+        var = std * std
+        return (-((action - mean) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(1)
+
+    @staticmethod
+    def convert_action_for_env(action: TEN) -> TEN:
+        return action.tanh()
+
+
+class CriticPPO(nn.Module, _StateNormMixin):
+    """State-value net: V = MLP(state_norm(s))."""
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int, activation: str = "gelu"):
+        super().__init__()
+        self.net = make_mlp([state_dim, *net_dims, 1], activation)
+        _init_output_layer(self.net[-1], std=0.5)
+        self.state_avg = nn.Parameter(th.zeros((state_dim,)), requires_grad=False)
+        self.state_std = nn.Parameter(th.ones((state_dim,)), requires_grad=False)
+        self.activation = activation
+
+    def forward(self, state: TEN) -> TEN:
+        return self.net(self.state_norm(state))

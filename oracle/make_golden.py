@@ -1,0 +1,301 @@
+"""Mint golden vectors for the on-policy hot path FROM THE IMPORTABLE PYTHON REFERENCE.  Test infrastructure.
+
+Runs only in the build container (needs ``/root/reference``); the GPU box consumes the committed
+``tests/golden/*.npz``.  Usage::
+
+    python oracle/make_golden.py            # rewrites tests/golden/*.npz
+
+What is recorded (SURVEY.md section 8(c) checkpoints), all produced by the UNMODIFIED reference classes
+``elegantrl.agents.AgentPPO`` (``elegantrl/agents/AgentPPO.py``) on CPU, float32:
+
+1. nets:     (state, action) -> actor mean / tanh action / logprob / entropy, critic value
+             (``ActorPPO.forward`` :363, ``get_logprob_entropy`` :378, ``CriticPPO.forward`` :435)
+2. gae:      (states, rewards, undones, unmasks, last_state) -> values, advantages, reward_sums, normalised
+             advantages, and the in-place mutated rewards / undones (``update_net`` :141-149,
+             ``get_advantages`` :207-232), for both scan branches
+3. update:   k consecutive ``update_objectives`` calls (:173-205) with the minibatch ids replayed from
+             ``th.manual_seed`` -> the three logged scalars per minibatch, post-update parameters and Adam
+             moments; plus a full ``update_net`` (:135-171) from the same start
+4. rollout:  ``_explore_vec_env`` (:87-129) on ``elegantrl_b200.envs.PendulumVecEnv`` (CPU torch) with the
+             policy noise replayed from ``th.manual_seed`` and the env's reset noise injected
+5. indices / masks: ids % H, ids // H, ~terminals, ~truncates are part of 2-4 and compared bit-exactly.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch as th
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = os.environ.get("ELEGANTRL_REFERENCE", "/root/reference")
+sys.path.insert(0, REFERENCE)
+sys.path.insert(0, REPO)
+
+from elegantrl.agents import AgentPPO as RefAgentPPO  # noqa: E402  (the reference)
+from elegantrl.train.config import Config as RefConfig  # noqa: E402
+from elegantrl_b200.envs import PendulumVecEnv  # noqa: E402
+
+OUT_DIR = os.path.join(REPO, "tests", "golden")
+
+
+def make_ref_agent(state_dim, action_dim, net_dims, num_envs, seed, **hyper):
+    th.manual_seed(seed)
+    env_args = {'env_name': 'golden', 'num_envs': num_envs, 'max_step': 200, 'state_dim': state_dim,
+                'action_dim': action_dim, 'if_discrete': False}
+    args = RefConfig(agent_class=RefAgentPPO, env_class=None, env_args=env_args)
+    args.net_dims = list(net_dims)
+    for k, v in hyper.items():
+        setattr(args, k, v)
+    agent = RefAgentPPO(list(net_dims), state_dim, action_dim, gpu_id=-1, args=args)
+    return agent
+
+
+def perturb_nets(agent, seed, std_log=-0.3, norm_stats=False):
+    """Move off the init point so that nothing is trivially zero (action_std_log, biases, norm stats)."""
+    g = th.Generator().manual_seed(seed)
+    with th.no_grad():
+        agent.act.action_std_log += std_log + 0.1 * th.randn(agent.act.action_std_log.shape, generator=g)
+        for net in (agent.act.net, agent.cri.net):
+            for layer in net:
+                if hasattr(layer, "bias"):
+                    layer.bias += 0.05 * th.randn(layer.bias.shape, generator=g)
+        if norm_stats:
+            avg = 0.3 * th.randn(agent.act.state_avg.shape, generator=g)
+            std = 0.5 + th.rand(agent.act.state_std.shape, generator=g)
+            for m in (agent.act, agent.cri):
+                m.state_avg[:] = avg
+                m.state_std[:] = std
+
+
+def dump_net(prefix, module, out):
+    linears = [m for m in module.net if isinstance(m, th.nn.Linear)]
+    out[f"{prefix}.n_layers"] = np.int64(len(linears))
+    for i, l in enumerate(linears):
+        out[f"{prefix}.W{i}"] = l.weight.detach().numpy().copy()
+        out[f"{prefix}.b{i}"] = l.bias.detach().numpy().copy()
+    out[f"{prefix}.state_avg"] = module.state_avg.detach().numpy().copy()
+    out[f"{prefix}.state_std"] = module.state_std.detach().numpy().copy()
+    if hasattr(module, "action_std_log"):
+        out[f"{prefix}.action_std_log"] = module.action_std_log.detach().numpy().copy()
+
+
+def dump_adam(prefix, optimizer, module, out):
+    linears = [m for m in module.net if isinstance(m, th.nn.Linear)]
+    params = [p for l in linears for p in (l.weight, l.bias)]
+    names = [n for i in range(len(linears)) for n in (f"W{i}", f"b{i}")]
+    if hasattr(module, "action_std_log"):
+        params.append(module.action_std_log)
+        names.append("action_std_log")
+    for p, n in zip(params, names):
+        st = optimizer.state[p]
+        out[f"{prefix}.m.{n}"] = st["exp_avg"].detach().numpy().copy()
+        out[f"{prefix}.v.{n}"] = st["exp_avg_sq"].detach().numpy().copy()
+        out[f"{prefix}.step"] = np.float64(float(st["step"]))
+
+
+def synth_buffer(agent, horizon_len, num_envs, seed, p_term=0.08, p_trunc=0.08):
+    g = th.Generator().manual_seed(seed)
+    s_dim, a_dim = agent.state_dim, agent.action_dim
+    states = th.randn((horizon_len, num_envs, s_dim), generator=g)
+    actions = 0.7 * th.randn((horizon_len, num_envs, a_dim), generator=g)
+    with th.no_grad():
+        logprobs = agent.act.get_logprob_entropy(states.reshape(-1, s_dim), actions.reshape(-1, a_dim))[0]
+        logprobs = logprobs.reshape(horizon_len, num_envs) + 0.05 * th.randn((horizon_len, num_envs), generator=g)
+    rewards = th.randn((horizon_len, num_envs), generator=g)
+    terminals = th.rand((horizon_len, num_envs), generator=g) < p_term
+    truncates = (th.rand((horizon_len, num_envs), generator=g) < p_trunc) & ~terminals
+    last_state = th.randn((num_envs, s_dim), generator=g)
+    return states, actions, logprobs, rewards, ~terminals, ~truncates, last_state
+
+
+def record_nets(agent, out, seed):
+    g = th.Generator().manual_seed(seed)
+    state = th.randn((37, agent.state_dim), generator=g) * 1.5
+    action = th.randn((37, agent.action_dim), generator=g)
+    with th.no_grad():
+        logprob, entropy = agent.act.get_logprob_entropy(state, action)
+        out["nets.state"] = state.numpy()
+        out["nets.action"] = action.numpy()
+        out["nets.actor_mean"] = agent.act.net(agent.act.state_norm(state)).numpy()
+        out["nets.actor_forward"] = agent.act(state).numpy()
+        out["nets.logprob"] = logprob.numpy()
+        out["nets.entropy"] = entropy.numpy()
+        out["nets.value"] = agent.cri(state).squeeze(1).numpy()
+
+
+def record_gae(agent, buf, out, tag):
+    states, actions, logprobs, rewards, undones, unmasks, last_state = [t.clone() for t in buf]
+    agent.last_state = last_state
+    with th.no_grad():
+        values = agent.cri(states).squeeze(-1)
+        advantages = agent.get_advantages(states, rewards, undones, unmasks, values)  # mutates rewards/undones
+        reward_sums = advantages + values
+        adv_norm = (advantages - advantages.mean()) / (advantages[::4, ::4].std() + 1e-5)
+    out[f"{tag}.values"] = values.numpy()
+    out[f"{tag}.last_value"] = agent.cri(last_state).detach().squeeze(-1).numpy()
+    out[f"{tag}.advantages"] = advantages.numpy()
+    out[f"{tag}.reward_sums"] = reward_sums.numpy()
+    out[f"{tag}.adv_norm"] = adv_norm.numpy()
+    out[f"{tag}.adv_mean"] = np.float64(advantages.mean().item())
+    out[f"{tag}.adv_std"] = np.float64(advantages[::4, ::4].std().item())
+    out[f"{tag}.rewards_after"] = rewards.numpy()
+    out[f"{tag}.undones_after"] = undones.numpy()
+    return states, actions, unmasks, logprobs, adv_norm, reward_sums
+
+
+def record_update(agent, train_buffer, out, num_updates, seed):
+    """k update_objectives calls with replayed ids, on a deep copy (the caller's agent stays untouched)."""
+    agent = copy.deepcopy(agent)
+    horizon_len, num_envs = train_buffer[0].shape[:2]
+    th.manual_seed(seed)
+    ids = th.stack([th.randint(horizon_len * num_envs, size=(agent.batch_size,)) for _ in range(num_updates)])
+    out["update.ids"] = ids.numpy()
+    out["update.ids0"] = th.fmod(ids, horizon_len).numpy()
+    out["update.ids1"] = th.div(ids, horizon_len, rounding_mode='floor').numpy()
+    th.manual_seed(seed)
+    scalars = []
+    with th.enable_grad():
+        for update_t in range(num_updates):
+            scalars.append(agent.update_objectives(train_buffer, update_t))
+            if update_t == 0:
+                dump_net("update.after1.actor", agent.act, out)
+                dump_net("update.after1.critic", agent.cri, out)
+    out["update.scalars"] = np.array(scalars, dtype=np.float64)
+    dump_net("update.after.actor", agent.act, out)
+    dump_net("update.after.critic", agent.cri, out)
+    dump_adam("update.after.actor_adam", agent.act_optimizer, agent.act, out)
+    dump_adam("update.after.critic_adam", agent.cri_optimizer, agent.cri, out)
+
+
+def record_update_net(agent, buf, out, seed):
+    """Full update_net from the raw rollout buffer (values + GAE + normalise + all minibatches)."""
+    agent = copy.deepcopy(agent)
+    states, actions, logprobs, rewards, undones, unmasks, last_state = [t.clone() for t in buf]
+    agent.last_state = last_state
+    horizon_len, num_envs = states.shape[:2]
+    update_times = int(horizon_len * agent.repeat_times / agent.batch_size)
+    th.manual_seed(seed)
+    ids = th.stack([th.randint(horizon_len * num_envs, size=(agent.batch_size,)) for _ in range(update_times)])
+    out["update_net.ids"] = ids.numpy()
+    th.manual_seed(seed)
+    result = agent.update_net([states, actions, logprobs, rewards, undones, unmasks])
+    th.set_grad_enabled(True)
+    out["update_net.result"] = np.array(result, dtype=np.float64)
+    dump_net("update_net.after.actor", agent.act, out)
+    dump_net("update_net.after.critic", agent.cri, out)
+
+
+def record_hyper(agent, out):
+    out["hp.gamma"] = np.float64(agent.gamma)
+    out["hp.lambda_gae_adv"] = np.float64(agent.lambda_gae_adv)
+    out["hp.ratio_clip"] = np.float64(agent.ratio_clip)
+    out["hp.lambda_entropy"] = np.float64(float(agent.lambda_entropy))
+    out["hp.clip_grad_norm"] = np.float64(agent.clip_grad_norm)
+    out["hp.learning_rate"] = np.float64(agent.learning_rate)
+    out["hp.reward_scale"] = np.float64(agent.reward_scale)
+    out["hp.batch_size"] = np.int64(agent.batch_size)
+    out["hp.repeat_times"] = np.float64(agent.repeat_times)
+    out["hp.if_use_v_trace"] = np.int64(int(agent.if_use_v_trace))
+
+
+def case_synthetic(name, state_dim, action_dim, net_dims, num_envs, horizon_len, seed, num_updates=3,
+                   norm_stats=False, **hyper):
+    out = {}
+    agent = make_ref_agent(state_dim, action_dim, net_dims, num_envs, seed, **hyper)
+    perturb_nets(agent, seed + 1, norm_stats=norm_stats)
+    record_hyper(agent, out)
+    out["dims"] = np.array([state_dim, action_dim, num_envs, horizon_len] + list(net_dims), dtype=np.int64)
+    dump_net("actor", agent.act, out)
+    dump_net("critic", agent.cri, out)
+    record_nets(agent, out, seed + 2)
+
+    buf = synth_buffer(agent, horizon_len, num_envs, seed + 3)
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks", "last_state"), buf):
+        out[f"buf.{k}"] = t.numpy().copy()
+    train_buffer = record_gae(agent, buf, out, "gae")
+    agent.if_use_v_trace = not agent.if_use_v_trace  # the other scan branch (AgentPPO.py:228-231)
+    record_gae(agent, buf, out, "gae_alt")
+    agent.if_use_v_trace = not agent.if_use_v_trace
+    record_update(agent, train_buffer, out, num_updates, seed + 4)
+    record_update_net(agent, buf, out, seed + 5)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def case_rollout(name, num_envs, horizon_len, max_step, seed, net_dims=(64, 64), **hyper):
+    """Reference _explore_vec_env + update_net on the torch Pendulum vec env (the bench workload, small)."""
+    out = {}
+    agent = make_ref_agent(3, 1, net_dims, num_envs, seed, **hyper)
+    perturb_nets(agent, seed + 1, std_log=-0.5)
+    record_hyper(agent, out)
+    out["dims"] = np.array([3, 1, num_envs, horizon_len] + list(net_dims), dtype=np.int64)
+    out["max_step"] = np.int64(max_step)
+    dump_net("actor", agent.act, out)
+    dump_net("critic", agent.cri, out)
+
+    env = PendulumVecEnv(num_envs=num_envs, gpu_id=-1, max_step=max_step, seed=seed)
+    g = th.Generator().manual_seed(seed + 2)
+    reset_noise = th.rand((horizon_len + 1, num_envs, 2), generator=g)
+    env.inject_reset_noise(reset_noise)
+    state, _ = env.reset()
+    # stagger episode phases so truncations land at different t for different envs
+    env.cur_step[:] = th.randint(0, max_step, (num_envs,), generator=g, dtype=th.int32)
+    out["env.theta0"] = env.theta.numpy().copy()
+    out["env.theta_dot0"] = env.theta_dot.numpy().copy()
+    out["env.cur_step0"] = env.cur_step.numpy().copy()
+    out["env.reset_noise"] = reset_noise[1:].numpy().copy()  # row t is consumed by step t
+    out["state0"] = state.numpy().copy()
+    agent.last_state = state
+
+    th.manual_seed(seed + 3)
+    eps = th.stack([th.randn((num_envs, 1)) for _ in range(horizon_len)])
+    out["eps"] = eps.numpy()
+    th.manual_seed(seed + 3)
+    with th.no_grad():
+        states, actions, logprobs, rewards, undones, unmasks = agent.explore_env(env, horizon_len)
+    # the replayed noise must be what Normal.sample() consumed
+    with th.no_grad():
+        mean0 = agent.act.net(agent.act.state_norm(states[0]))
+    assert th.equal(actions[0], mean0 + agent.act.action_std_log.exp() * eps[0]), "noise replay mismatch"
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks"),
+                    (states, actions, logprobs, rewards, undones, unmasks)):
+        out[f"rollout.{k}"] = t.numpy().copy()
+    out["rollout.last_state"] = agent.last_state.numpy().copy()
+    out["rollout.theta"] = env.theta.numpy().copy()
+    out["rollout.theta_dot"] = env.theta_dot.numpy().copy()
+    out["rollout.cur_step"] = env.cur_step.numpy().copy()
+
+    buf = (states, actions, logprobs, rewards, undones, unmasks, agent.last_state.clone())
+    record_gae(agent, buf, out, "gae")
+    record_update_net(agent, buf, out, seed + 5)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    # BASELINE config-2 dims (Pendulum, 2x64), small N/H, non-trivial norm stats
+    case_synthetic("synth_s3_a1_64x64", 3, 1, (64, 64), num_envs=16, horizon_len=24, seed=11,
+                   batch_size=32, repeat_times=4, norm_stats=True)
+    # LunarLanderContinuous dims (BASELINE config 5), demo net_dims style
+    case_synthetic("synth_s8_a2_128x64", 8, 2, (128, 64), num_envs=12, horizon_len=20, seed=23,
+                   batch_size=48, repeat_times=8, gamma=0.97, lambda_entropy=0.04, learning_rate=2e-4,
+                   ratio_clip=0.4)
+    # three hidden layers, ragged N/H (lattice [::4, ::4] edge), reward_scale != 1
+    case_synthetic("synth_s5_a3_64x48x32", 5, 3, (64, 48, 32), num_envs=10, horizon_len=9, seed=37,
+                   batch_size=16, repeat_times=4, clip_grad_norm=0.5, lambda_gae_adv=0.9)
+    # N == 1 (single env shapes [H, 1, ...]) -- reference _explore_one_env reshapes to this (:78-84)
+    case_synthetic("synth_s3_a1_n1", 3, 1, (32, 32), num_envs=1, horizon_len=64, seed=41,
+                   batch_size=16, repeat_times=2)
+    # the bench workload in miniature: fused rollout + update_net
+    case_rollout("rollout_pendulum_n32_h40", num_envs=32, horizon_len=40, max_step=25, seed=53,
+                 batch_size=64, repeat_times=8, reward_scale=0.25)
+    case_rollout("rollout_pendulum_n8_h16", num_envs=8, horizon_len=16, max_step=200, seed=61,
+                 batch_size=16, repeat_times=4)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,420 @@
+"""CPU oracle for the on-policy hot path (rollout -> GAE -> PPO update).  TEST INFRASTRUCTURE ONLY.
+
+A numpy restatement (closed form, hand-written backward, no autograd, no torch) of the arithmetic of the
+reference's on-policy agent.  Every function cites the reference file:line it follows (paths relative to
+the reference checkout, ``elegantrl/...``).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` leg of ``bench.py`` may import this module; the product path (``elegantrl_b200``) never
+does, and fails loudly when ``libb200rl.so`` is missing.
+
+Pinning: the reference's own tests hold no numeric goldens for this path, so the oracle
+is pinned against vectors minted *from the importable Python reference itself* by ``oracle/make_golden.py``
+(committed under ``tests/golden/``) -- see ``tests/test_oracle_golden.py``.
+
+Conventions
+-----------
+* a "net" is a dict ``{"W": [W0, W1, ...], "b": [b0, b1, ...], "state_avg", "state_std",
+  "action_std_log" (actor only, shape [1, A]), "activation": "gelu" | "relu"}``; ``W[l]`` has the
+  ``nn.Linear.weight`` layout ``[out, in]``.
+* dtype: everything is computed in the dtype of the inputs (float32 to mirror the reference, float64 for
+  a higher-precision yardstick); integer / mask paths are exact.
+"""
+import math
+
+import numpy as np
+from scipy.special import erf as _erf
+
+SQRT_HALF = math.sqrt(0.5)
+INV_SQRT_2PI = 1.0 / math.sqrt(2.0 * math.pi)
+LOG_SQRT_2PI = math.log(math.sqrt(2.0 * math.pi))
+
+
+# ----------------------------------------------------------------------------------------------- nets
+def act_fn(z, activation):
+    """nn.GELU() (exact erf form) / nn.ReLU -- reference AgentBase.py:353-354 (build_mlp default GELU)."""
+    if activation == "gelu":
+        return (z * 0.5 * (1.0 + _erf(z * SQRT_HALF))).astype(z.dtype)
+    if activation == "relu":
+        return np.maximum(z, 0).astype(z.dtype)
+    raise ValueError(activation)
+
+
+def act_grad(z, activation):
+    """d act / d z.  GELU' = Phi(z) + z * phi(z)."""
+    if activation == "gelu":
+        cdf = 0.5 * (1.0 + _erf(z * SQRT_HALF))
+        pdf = np.exp(-0.5 * z * z) * INV_SQRT_2PI
+        return (cdf + z * pdf).astype(z.dtype)
+    if activation == "relu":
+        return (z > 0).astype(z.dtype)
+    raise ValueError(activation)
+
+
+def state_norm(net, state):
+    """(s - avg) / (std + 1e-4) -- reference AgentPPO.py:360-361 (actor) / :440-441 (critic)."""
+    dt = state.dtype
+    if net.get("state_avg") is None:
+        return state
+    return ((state - net["state_avg"].astype(dt)) / (net["state_std"].astype(dt) + dt.type(1e-4))).astype(dt)
+
+
+def mlp_forward(net, x, keep=False):
+    """Linear-act-...-Linear on an already-normalised input x [B, in] -- reference AgentBase.py:345-360."""
+    acts, pre = [x], []
+    h = x
+    n_layers = len(net["W"])
+    for l in range(n_layers):
+        z = (h @ net["W"][l].astype(x.dtype).T + net["b"][l].astype(x.dtype)).astype(x.dtype)
+        pre.append(z)
+        h = act_fn(z, net["activation"]) if l < n_layers - 1 else z
+        acts.append(h)
+    return (h, acts, pre) if keep else h
+
+
+def mlp_backward(net, acts, pre, d_out):
+    """Hand-written backward of ``mlp_forward``: returns (dW list, db list, d_input)."""
+    n_layers = len(net["W"])
+    dW, db = [None] * n_layers, [None] * n_layers
+    dz = d_out
+    for l in range(n_layers - 1, -1, -1):
+        dW[l] = (dz.T @ acts[l]).astype(dz.dtype)
+        db[l] = dz.sum(axis=0).astype(dz.dtype)
+        dx = (dz @ net["W"][l].astype(dz.dtype)).astype(dz.dtype)
+        if l > 0:
+            dz = (dx * act_grad(pre[l - 1], net["activation"])).astype(dz.dtype)
+    return dW, db, dx
+
+
+def critic_value(critic, state):
+    """CriticPPO.forward -- reference AgentPPO.py:435-438.  state [..., S] -> value [...]."""
+    lead = state.shape[:-1]
+    v = mlp_forward(critic, state_norm(critic, state.reshape(-1, state.shape[-1])))
+    return v.reshape(lead)
+
+
+def actor_mean(actor, state):
+    """action_avg = net(state_norm(s)) -- reference AgentPPO.py:369-370."""
+    return mlp_forward(actor, state_norm(actor, state))
+
+
+def actor_forward(actor, state):
+    """ActorPPO.forward (deterministic, tanh) -- reference AgentPPO.py:363-366."""
+    return np.tanh(actor_mean(actor, state))
+
+
+def gaussian_logprob(mean, std_log, action):
+    """Normal(mean, exp(std_log)).log_prob(action).sum(1) -- reference AgentPPO.py:371-375 +
+    torch.distributions.Normal.log_prob: -((x-mu)^2)/(2 var) - log(scale) - log(sqrt(2 pi))."""
+    dt = mean.dtype
+    std = np.exp(std_log.astype(dt))
+    var = std * std
+    lp = -((action - mean) ** 2) / (2 * var) - np.log(std) - dt.type(LOG_SQRT_2PI)
+    return lp.sum(axis=1).astype(dt)
+
+
+def gaussian_entropy(std_log, batch, dt):
+    """Normal.entropy().sum(1) = sum_a (0.5 + 0.5 log 2pi + log scale) -- reference AgentPPO.py:385."""
+    std = np.exp(std_log.astype(dt))
+    ent = (dt.type(0.5 + 0.5 * math.log(2 * math.pi)) + np.log(std)).sum()
+    return np.full((batch,), ent, dtype=dt)
+
+
+def sample_action(actor, state, eps):
+    """ActorPPO.get_action with the noise injected: a = mu + sigma * eps -- reference AgentPPO.py:368-376
+    (torch draws Normal.sample() as randn * sigma + mu)."""
+    mean = actor_mean(actor, state)
+    std = np.exp(actor["action_std_log"].astype(mean.dtype))
+    action = (eps.astype(mean.dtype) * std + mean).astype(mean.dtype)
+    return action, gaussian_logprob(mean, actor["action_std_log"], action)
+
+
+def logprob_entropy(actor, state, action):
+    """ActorPPO.get_logprob_entropy -- reference AgentPPO.py:378-386."""
+    mean = actor_mean(actor, state)
+    return (gaussian_logprob(mean, actor["action_std_log"], action),
+            gaussian_entropy(actor["action_std_log"], state.shape[0], mean.dtype))
+
+
+# ------------------------------------------------------------------------------------------------ env
+def pendulum_observe(theta, theta_dot):
+    return np.stack((np.cos(theta), np.sin(theta), theta_dot), axis=1).astype(theta.dtype)
+
+
+def pendulum_step(theta, theta_dot, cur_step, env_action, reset_u, max_step=200):
+    """One step of ``elegantrl_b200.envs.PendulumVecEnv.step`` (gymnasium Pendulum-v1 physics with the
+    scaling of reference elegantrl/envs/CustomGymEnv.py:39-44: torque = 2 * action, reward * 0.5;
+    truncation at max_step, auto-reset -- contract of reference elegantrl/train/config.py:243-247).
+    env_action [N] already tanh'ed.  reset_u [N, 2] in [0, 1).  Returns new (theta, theta_dot, cur_step),
+    reward, terminal, truncate."""
+    dt = theta.dtype
+    f = dt.type
+    torque = np.clip(env_action.astype(dt) * f(2.0), f(-2.0), f(2.0))
+    theta_norm = np.remainder(theta + f(math.pi), f(2 * math.pi)) - f(math.pi)
+    cost = theta_norm * theta_norm + f(0.1) * (theta_dot * theta_dot) + f(0.001) * (torque * torque)
+    reward = (cost * f(-0.5)).astype(dt)
+    accel = f(15.0) * np.sin(theta) + f(3.0) * torque
+    new_theta_dot = np.clip(theta_dot + accel * f(0.05), f(-8.0), f(8.0)).astype(dt)
+    new_theta = (theta + new_theta_dot * f(0.05)).astype(dt)
+    cur_step = cur_step + 1
+    truncate = cur_step >= max_step
+    terminal = np.zeros_like(truncate)
+    u = reset_u.astype(dt)
+    new_theta = np.where(truncate, (u[:, 0] * f(2.0) - f(1.0)) * f(math.pi), new_theta).astype(dt)
+    new_theta_dot = np.where(truncate, u[:, 1] * f(2.0) - f(1.0), new_theta_dot).astype(dt)
+    cur_step = np.where(truncate, 0, cur_step).astype(np.int32)
+    return new_theta, new_theta_dot, cur_step, reward, terminal, truncate
+
+
+def rollout_pendulum(actor, critic, theta, theta_dot, cur_step, horizon_len, eps, reset_u,
+                     reward_scale=1.0, max_step=200):
+    """AgentPPO._explore_vec_env on the Pendulum vec env -- reference AgentPPO.py:87-129: record pre-step
+    state, raw (pre-tanh) action, logprob; env gets tanh(action); rewards *= reward_scale;
+    undones = ~terminals; unmasks = ~truncates.  Also returns V(s_t) of the pre-update critic
+    (what reference update_net :141-143 recomputes) and the final env state."""
+    dt = theta.dtype
+    n = theta.shape[0]
+    a_dim = actor["W"][-1].shape[0]
+    states = np.zeros((horizon_len, n, 3), dt)
+    actions = np.zeros((horizon_len, n, a_dim), dt)
+    logprobs = np.zeros((horizon_len, n), dt)
+    rewards = np.zeros((horizon_len, n), dt)
+    terminals = np.zeros((horizon_len, n), bool)
+    truncates = np.zeros((horizon_len, n), bool)
+    values = np.zeros((horizon_len, n), dt)
+    for t in range(horizon_len):
+        state = pendulum_observe(theta, theta_dot)
+        action, logprob = sample_action(actor, state, eps[t])
+        states[t], actions[t], logprobs[t] = state, action, logprob
+        if critic is not None:
+            values[t] = critic_value(critic, state)
+        theta, theta_dot, cur_step, reward, terminal, truncate = pendulum_step(
+            theta, theta_dot, cur_step, np.tanh(action[:, 0]), reset_u[t], max_step)
+        rewards[t], terminals[t], truncates[t] = reward, terminal, truncate
+    rewards = (rewards * dt.type(reward_scale)).astype(dt)
+    out = dict(states=states, actions=actions, logprobs=logprobs, rewards=rewards,
+               undones=~terminals, unmasks=~truncates, values=values,
+               last_state=pendulum_observe(theta, theta_dot), theta=theta, theta_dot=theta_dot, cur_step=cur_step)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GAE
+def gae(rewards, undones, unmasks, values, last_value, gamma, lambda_gae, if_use_v_trace=True,
+        trunc_values=None):
+    """AgentPPO.get_advantages -- reference AgentPPO.py:207-232.
+
+    (i) truncation fix-up, IN PLACE on the caller's arrays (:211-214): rewards[trunc] += V(s_trunc);
+        undones[trunc] = False.  ``trunc_values`` = V at the stored (pre-reset) state; it equals ``values``
+        because the same critic produced both (:143 vs :213).
+    (ii) masks = undones * gamma (:216); (iii) next_value = V(last_state) (:219-220);
+    (iv) reverse scan, default branch :223-227, alternative branch :228-231."""
+    dt = values.dtype
+    if trunc_values is None:
+        trunc_values = values
+    truncated = np.logical_not(unmasks)
+    if truncated.any():
+        rewards[truncated] += trunc_values[truncated]
+        undones[truncated] = False
+    masks = (undones * dt.type(gamma)).astype(dt)
+    horizon_len = rewards.shape[0]
+    advantages = np.empty_like(values)
+    next_value = last_value.astype(dt).copy()
+    advantage = np.zeros_like(next_value)
+    lam = dt.type(lambda_gae)
+    if if_use_v_trace:
+        for t in range(horizon_len - 1, -1, -1):
+            next_value = rewards[t] + masks[t] * next_value
+            advantages[t] = advantage = next_value - values[t] + masks[t] * lam * advantage
+            next_value = values[t]
+    else:
+        for t in range(horizon_len - 1, -1, -1):
+            advantages[t] = rewards[t] - values[t] + masks[t] * advantage
+            advantage = values[t] + lam * advantages[t]
+    return advantages
+
+
+def advantage_stats(advantages):
+    """mean over everything, unbiased std over the [::4, ::4] sub-lattice -- reference AgentPPO.py:149."""
+    mean = advantages.mean(dtype=np.float64)
+    std = advantages[::4, ::4].std(ddof=1, dtype=np.float64)
+    return mean, std
+
+
+def normalize_advantages(advantages):
+    """(adv - adv.mean()) / (adv[::4, ::4].std() + 1e-5) -- reference AgentPPO.py:149."""
+    dt = advantages.dtype
+    mean, std = advantage_stats(advantages)
+    return ((advantages - dt.type(mean)) / (dt.type(std) + dt.type(1e-5))).astype(dt)
+
+
+def values_gae_pass(critic, states, rewards, undones, unmasks, last_state, gamma, lambda_gae,
+                    if_use_v_trace=True):
+    """First half of AgentPPO.update_net -- reference AgentPPO.py:139-150: values, advantages (mutating
+    rewards/undones), reward_sums = adv + values, normalised advantages."""
+    values = critic_value(critic, states)
+    last_value = critic_value(critic, last_state)
+    advantages = gae(rewards, undones, unmasks, values, last_value, gamma, lambda_gae, if_use_v_trace)
+    reward_sums = (advantages + values).astype(values.dtype)
+    return values, advantages, reward_sums, normalize_advantages(advantages)
+
+
+# --------------------------------------------------------------------------------------------- update
+def split_ids(ids, horizon_len):
+    """ids0 = ids % H (time), ids1 = ids // H (env) -- reference AgentPPO.py:178-180.  Exact (int64)."""
+    return np.fmod(ids, horizon_len), ids // horizon_len
+
+
+def new_adam_state(net, has_std):
+    st = {"step": 0, "m_W": [np.zeros_like(w) for w in net["W"]], "v_W": [np.zeros_like(w) for w in net["W"]],
+          "m_b": [np.zeros_like(b) for b in net["b"]], "v_b": [np.zeros_like(b) for b in net["b"]]}
+    if has_std:
+        st["m_std"] = np.zeros_like(net["action_std_log"])
+        st["v_std"] = np.zeros_like(net["action_std_log"])
+    return st
+
+
+def clip_grads(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ -- called per net by reference AgentBase.py:239-248:
+    coef = max_norm / (total_norm + 1e-6), clamped to <= 1, multiplied into every grad."""
+    dt = grads[0].dtype
+    total_norm = dt.type(math.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads)))
+    if max_norm is None or max_norm <= 0:
+        return grads, total_norm
+    coef = min(dt.type(max_norm) / (total_norm + dt.type(1e-6)), dt.type(1.0))
+    return [(g * coef).astype(dt) for g in grads], total_norm
+
+
+def adam_step(params, grads, ms, vs, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam (defaults: no weight decay / amsgrad), op order of torch's ``_single_tensor_adam``:
+    m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g*g; denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= lr/(1-b1^t) * m/denom.
+    Instantiated by reference AgentPPO.py:24-25, stepped by AgentBase.py:248."""
+    step = step + 1
+    bc1 = 1.0 - beta1 ** step
+    bc2_sqrt = math.sqrt(1.0 - beta2 ** step)
+    step_size = lr / bc1
+    for p, g, m, v in zip(params, grads, ms, vs):
+        dt = p.dtype
+        m += (g - m) * dt.type(1.0 - beta1)
+        v *= dt.type(beta2)
+        v += dt.type(1.0 - beta2) * g * g
+        denom = np.sqrt(v) / dt.type(bc2_sqrt) + dt.type(eps)
+        p -= dt.type(step_size) * (m / denom)
+    return step
+
+
+def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
+    """AgentPPO.update_objectives on an already-gathered minibatch -- reference AgentPPO.py:189-205 +
+    AgentBase.optimizer_backward :239-248.  ``batch`` = dict(state, action, unmask (bool), logprob,
+    advantage (normalised), reward_sum).  ``hp`` = dict(ratio_clip, lambda_entropy, clip_grad_norm,
+    learning_rate).  Mutates nets and Adam states in place.  Returns the three logged scalars and a dict of
+    the (clipped) gradients for inspection."""
+    state, action = batch["state"], batch["action"]
+    dt = state.dtype
+    unmask = batch["unmask"].astype(dt)
+    bsz = dt.type(state.shape[0])
+
+    # critic: obj_critic = mean(MSE(V(s), reward_sum) * unmask)   (:189-191)
+    xc = state_norm(critic, state)
+    value, acts_c, pre_c = mlp_forward(critic, xc, keep=True)
+    err = value[:, 0] - batch["reward_sum"]
+    obj_critic = (err * err * unmask).mean(dtype=dt)
+    d_value = (dt.type(2.0) * err * unmask / bsz)[:, None].astype(dt)
+    dWc, dbc, _ = mlp_backward(critic, acts_c, pre_c, d_value)
+    gc = [g for pair in zip(dWc, dbc) for g in pair]
+    gc, norm_c = clip_grads(gc, hp["clip_grad_norm"])
+
+    # actor: ratio, "clip" as a constant factor, entropy sign as in the reference   (:193-204)
+    xa = state_norm(actor, state)
+    mean, acts_a, pre_a = mlp_forward(actor, xa, keep=True)
+    std_log = actor["action_std_log"].astype(dt)
+    std = np.exp(std_log)
+    var = std * std
+    diff = action - mean
+    new_logprob = (-(diff ** 2) / (2 * var) - np.log(std) - dt.type(LOG_SQRT_2PI)).sum(axis=1)
+    entropy = gaussian_entropy(std_log, state.shape[0], dt)
+    ratio = np.exp(new_logprob - batch["logprob"])
+    adv = batch["advantage"]
+    kappa = np.where(adv > 0, dt.type(1 - hp["ratio_clip"]), dt.type(1 + hp["ratio_clip"])).astype(dt)
+    surrogate = adv * ratio * kappa
+    obj_surrogate = (surrogate * unmask).mean(dtype=dt)
+    obj_entropy = (entropy * unmask).mean(dtype=dt)
+    lam_ent = dt.type(hp["lambda_entropy"])
+    # loss = -(obj_surrogate - obj_entropy * lambda_entropy)
+    g_logp = (-(surrogate * unmask) / bsz).astype(dt)                      # d loss / d new_logprob
+    d_mean = (g_logp[:, None] * diff / var).astype(dt)                      # d logp / d mu = (a - mu) / var
+    d_std_log = (g_logp[:, None] * (diff * diff / var - dt.type(1.0))).sum(axis=0, keepdims=True) \
+        + lam_ent * unmask.mean(dtype=dt)                                   # d entropy / d std_log = 1
+    dWa, dba, _ = mlp_backward(actor, acts_a, pre_a, d_mean)
+    ga = [g for pair in zip(dWa, dba) for g in pair] + [d_std_log.astype(dt)]
+    ga, norm_a = clip_grads(ga, hp["clip_grad_norm"])
+
+    # Adam, critic first (:191) then actor (:204); the nets are disjoint so the order is immaterial
+    pc = [p for pair in zip(critic["W"], critic["b"]) for p in pair]
+    mc = [p for pair in zip(opt_c["m_W"], opt_c["m_b"]) for p in pair]
+    vc = [p for pair in zip(opt_c["v_W"], opt_c["v_b"]) for p in pair]
+    opt_c["step"] = adam_step(pc, gc, mc, vc, opt_c["step"], hp["learning_rate"])
+    pa = [p for pair in zip(actor["W"], actor["b"]) for p in pair] + [actor["action_std_log"]]
+    ma = [p for pair in zip(opt_a["m_W"], opt_a["m_b"]) for p in pair] + [opt_a["m_std"]]
+    va = [p for pair in zip(opt_a["v_W"], opt_a["v_b"]) for p in pair] + [opt_a["v_std"]]
+    opt_a["step"] = adam_step(pa, ga, ma, va, opt_a["step"], hp["learning_rate"])
+    return (float(obj_critic), float(obj_surrogate), float(obj_entropy)), \
+        dict(critic=gc, actor=ga, norm_critic=float(norm_c), norm_actor=float(norm_a))
+
+
+def gather_minibatch(buffer, ids, adv_mean=None, adv_std=None):
+    """The six advanced-index gathers of reference AgentPPO.py:178-187.  ``buffer`` = dict(states [H,N,S],
+    actions [H,N,A], unmasks, logprobs, advantages, reward_sums [H,N]).  If adv_mean/adv_std are given the
+    advantage is normalised at gather time (what the CUDA engine does) instead of beforehand."""
+    horizon_len = buffer["states"].shape[0]
+    ids0, ids1 = split_ids(ids, horizon_len)
+    adv = buffer["advantages"][ids0, ids1]
+    if adv_mean is not None:
+        dt = adv.dtype
+        adv = ((adv - dt.type(adv_mean)) / (dt.type(adv_std) + dt.type(1e-5))).astype(dt)
+    return dict(state=buffer["states"][ids0, ids1], action=buffer["actions"][ids0, ids1],
+                unmask=buffer["unmasks"][ids0, ids1], logprob=buffer["logprobs"][ids0, ids1],
+                advantage=adv, reward_sum=buffer["reward_sums"][ids0, ids1])
+
+
+def update_net(actor, critic, opt_a, opt_c, rollout, last_state, ids_per_update, hp):
+    """AgentPPO.update_net -- reference AgentPPO.py:135-171, with the minibatch indices injected
+    (``ids_per_update`` [update_times, batch_size] int64 replaces th.randint :178).
+    update_times = int(H * repeat_times / batch_size) is the caller's business (:159)."""
+    states = rollout["states"]
+    values, advantages, reward_sums, adv_norm = values_gae_pass(
+        critic, states, rollout["rewards"], rollout["undones"], rollout["unmasks"], last_state,
+        hp["gamma"], hp["lambda_gae_adv"], hp.get("if_use_v_trace", True))
+    buffer = dict(states=states, actions=rollout["actions"], unmasks=rollout["unmasks"],
+                  logprobs=rollout["logprobs"], advantages=adv_norm, reward_sums=reward_sums)
+    logs = []
+    for ids in ids_per_update:
+        scalars, _ = ppo_minibatch(actor, critic, opt_a, opt_c, gather_minibatch(buffer, ids), hp)
+        logs.append(scalars)
+    logs = np.array(logs, dtype=np.float64)
+    return tuple(logs.mean(axis=0)), dict(values=values, advantages=advantages, reward_sums=reward_sums,
+                                          adv_norm=adv_norm, per_update=logs)
+
+
+# ------------------------------------------------------------------------------------------ utilities
+def net_from_torch(module, dtype=np.float32):
+    """Copy a torch ActorPPO / CriticPPO (reference's or this repo's: same attribute names) to a net dict."""
+    import torch.nn as nn
+    linears = [m for m in module.net if isinstance(m, nn.Linear)]
+    activation = "relu" if any(isinstance(m, nn.ReLU) for m in module.net) else "gelu"
+    net = {"W": [l.weight.detach().cpu().numpy().astype(dtype).copy() for l in linears],
+           "b": [l.bias.detach().cpu().numpy().astype(dtype).copy() for l in linears],
+           "activation": activation, "state_avg": None, "state_std": None}
+    if hasattr(module, "state_avg"):
+        net["state_avg"] = module.state_avg.detach().cpu().numpy().astype(dtype).copy()
+        net["state_std"] = module.state_std.detach().cpu().numpy().astype(dtype).copy()
+    if hasattr(module, "action_std_log"):
+        net["action_std_log"] = module.action_std_log.detach().cpu().numpy().astype(dtype).copy()
+    return net
+
+
+def net_astype(net, dtype):
+    out = dict(net)
+    out["W"] = [w.astype(dtype) for w in net["W"]]
+    out["b"] = [b.astype(dtype) for b in net["b"]]
+    for k in ("state_avg", "state_std", "action_std_log"):
+        if net.get(k) is not None:
+            out[k] = net[k].astype(dtype)
+    return out
