@@ -1,0 +1,282 @@
+"""Benchmark of the on-policy hot path: env-steps/sec over full cycles (rollout -> GAE -> PPO update).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's engine, N GPUs of one node
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (PyTorch-CPU port, host cores)
+
+Workload (BASELINE.json configs[1]): AgentPPO on Pendulum-v1, 65 536 envs PER GPU
+(env-sharded, weak scaling), horizon 128, 2x64 GELU MLP actor + critic, Config defaults batch_size=128,
+repeat_times=8 -> 8 minibatch updates per cycle.  One "step" = explore_env(env, 128) + update_net(buffer).
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for how each field is produced.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+NUM_ENVS = 65536
+HORIZON = 128
+NET_DIMS = [64, 64]
+BATCH_SIZE = 128
+REPEAT_TIMES = 8.0
+METRIC = "env-steps/sec (rollout+GAE+update) at 65 536 envs"
+UNIT = "env-steps/s"
+FLOP_PER_ENV_STEP = 17408          # actor fwd 8704 + critic fwd 8704
+HBM_BYTES_PER_ENV_STEP = 30        # 26 B trajectory + 4 B value written by the fused rollout kernel
+
+
+def workload_config(n_gpus):
+    return {"workload": "AgentPPO Pendulum-v1, 65 536 envs per GPU, horizon 128, 2x64 GELU MLP (BASELINE configs[1])",
+            "num_envs_per_gpu": NUM_ENVS, "num_envs_total": NUM_ENVS * n_gpus, "horizon_len": HORIZON,
+            "net_dims": NET_DIMS, "batch_size": BATCH_SIZE, "repeat_times": REPEAT_TIMES,
+            "update_times": int(HORIZON * REPEAT_TIMES / BATCH_SIZE), "parallelism": f"env-shard x{n_gpus}",
+            "l2": "each step writes a fresh 252 MB trajectory (> 126 MB L2); no explicit flush needed",
+            "rng": "Philox4x32-10 on device (policy noise, env resets, minibatch indices)"}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json (hbm copy; cuBLAS bf16 sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, source="fallback of B200_PROFILING.md")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, sm_max, reasons, power = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); sm_max.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(sm_max), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle/cpu_port.py restates its ATen op sequence), all host
+    threads, same config / metric; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch as th
+    from oracle.cpu_port import CpuPPO
+    from elegantrl_b200.envs import PendulumVecEnv
+    threads = th.get_num_threads()
+    th.manual_seed(0)
+    agent = CpuPPO(NET_DIMS, 3, 1, NUM_ENVS, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+    env = PendulumVecEnv(num_envs=NUM_ENVS, gpu_id=-1, max_step=200, seed=0)
+    agent.last_state = env.reset()[0]
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        buffer = agent.explore_env(env, HORIZON)
+        agent.update_net(list(buffer))
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = NUM_ENVS * HORIZON * len(times) / total
+    sample = f"{len(times)} full cycles (65 536 envs x 128 steps + update) after {args.warmup} warm-up, {threads} torch threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_engine(args):
+    import torch as th
+    import torch.distributed as dist
+    from elegantrl_b200 import Config, _lib
+    from elegantrl_b200.agents import AgentPPO
+    from elegantrl_b200.envs import PendulumVecEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    th.cuda.set_device(local_rank)
+    dev = th.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    env_args = {'env_name': 'Pendulum-v1', 'num_envs': NUM_ENVS, 'max_step': 200, 'state_dim': 3, 'action_dim': 1,
+                'if_discrete': False}
+    cfg = Config(AgentPPO, PendulumVecEnv, env_args)
+    cfg.net_dims, cfg.batch_size, cfg.repeat_times, cfg.random_seed = NET_DIMS, BATCH_SIZE, REPEAT_TIMES, 0
+    th.manual_seed(0)  # identical initial parameters on every rank
+    agent = AgentPPO(NET_DIMS, 3, 1, gpu_id=local_rank, args=cfg)
+    if world > 1:
+        agent.enable_data_parallel()
+    env = PendulumVecEnv(num_envs=NUM_ENVS, gpu_id=local_rank, max_step=200, seed=rank)
+    agent.last_state = env.reset()[0]
+    # stagger episode phases like a long-running job (otherwise every env truncates at the same step)
+    env.cur_step[:] = th.randint(0, 200, (NUM_ENVS,), device=dev, dtype=th.int32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    def cycle_device():
+        buffer = agent.explore_env(env, HORIZON)
+        return agent.update_net_device(list(buffer))
+
+    # pinned host mirrors for the end-to-end arm: env state in, last_state + 3 scalars out
+    host_in = [th.empty(NUM_ENVS, dtype=dt).pin_memory() for dt in (th.float32, th.float32, th.int32)]
+    host_last_state = th.empty((NUM_ENVS, 3), dtype=th.float32).pin_memory()
+    for h, d in zip(host_in, env.engine_state()):
+        h.copy_(d)
+
+    def cycle_e2e():
+        theta, theta_dot, cur_step = env.engine_state()
+        theta.copy_(host_in[0], non_blocking=True)          # H2D: the step's inputs from pinned host memory
+        theta_dot.copy_(host_in[1], non_blocking=True)
+        cur_step.copy_(host_in[2], non_blocking=True)
+        buffer = agent.explore_env(env, HORIZON)             # public API
+        result = agent.update_net(list(buffer))              # public API: returns 3 Python floats (D2H + sync)
+        host_last_state.copy_(agent.last_state, non_blocking=True)
+        for h, d in zip(host_in, env.engine_state()):        # D2H: env state for the host-side loop
+            h.copy_(d, non_blocking=True)
+        th.cuda.synchronize()
+        return result
+
+    for _ in range(max(args.warmup, 3)):
+        cycle_device()
+    barrier()
+
+    # ---- timed region 1: `value` -- inputs resident in HBM, no host round trips inside
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.b200rl_launch_count()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    roll_events = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        a.record()
+        buffer = agent.explore_env(env, HORIZON)
+        b.record()
+        roll_events.append((a, b))
+        out = agent.update_net_device(list(buffer))
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.b200rl_launch_count() - launches0
+    rollout_ms = statistics.mean(a.elapsed_time(b) for a, b in roll_events)
+    assert th.isfinite(out).all(), "non-finite losses"
+    t = th.tensor([elapsed_ms], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+
+    # ---- timed region 2: `e2e` -- public API with host buffers, H2D / D2H inside
+    for _ in range(2):
+        cycle_e2e()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        cycle_e2e()
+    ev1.record()
+    barrier()
+    t = th.tensor([ev0.elapsed_time(ev1)], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    env_steps = NUM_ENVS * HORIZON * args.steps * world
+    value = env_steps / (elapsed_ms * 1e-3)
+    peaks = measured_peaks()
+    per_launch_env_steps = NUM_ENVS * HORIZON
+    flops = FLOP_PER_ENV_STEP * per_launch_env_steps + 8704 * NUM_ENVS  # + V(last_state)
+    achieved_tflops = flops / (rollout_ms * 1e-3) / 1e12
+    hbm_gbs = HBM_BYTES_PER_ENV_STEP * per_launch_env_steps / (rollout_ms * 1e-3) / 1e9
+    roofline = {"kernel": "rollout_pendulum_kernel (fused env + actor + critic + trajectory stores)", "bound": "tensor",
+                "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": rollout_ms,
+                "share_of_step": rollout_ms / (elapsed_ms / args.steps),
+                "pipe": "fp32 FFMA (CUDA cores); tensor-pipe peak is the denominator north_star asks for",
+                "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                        "bytes_per_env_step": HBM_BYTES_PER_ENV_STEP}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": env_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": 3 * NUM_ENVS * 4, "d2h_bytes_per_step": 3 * 4 + NUM_ENVS * 3 * 4 + 3 * NUM_ENVS * 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_port import time_cpu_cycles
+        cb = time_cpu_cycles(NUM_ENVS, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, batch_size=BATCH_SIZE,
+                             repeat_times=REPEAT_TIMES)
+        line["cpu_baseline"] = {"value": cb["env_steps_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
+                                "sample": f"{cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up; "
+                                          f"explore {statistics.mean(cb['explore_s']):.3f}s + update {statistics.mean(cb['update_s']):.3f}s per cycle"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-cycles", type=int, default=4, help="CPU-baseline sample size (full cycles)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

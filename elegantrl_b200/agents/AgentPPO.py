@@ -1,0 +1,435 @@
+"""Drop-in ``AgentPPO`` whose hot path runs in ``libb200rl.so`` (hand-written sm_100a CUDA).
+
+Boundary mirrored: the duck-typed Agent API the reference's training loops call --
+``agent_class(net_dims, state_dim, action_dim, gpu_id, args)``, ``explore_env(env, horizon_len) -> 6 tensors``,
+``update_net(buffer) -> 3 floats``, ``act`` / ``cri`` as picklable ``nn.Module`` s, ``last_state``, ``device``,
+``explore_rate``, ``if_off_policy``, ``save_or_load_agent`` (reference ``elegantrl/train/run.py:47, 104, 125-126,
+136``; agent ``elegantrl/agents/AgentPPO.py:12-232``; base ``elegantrl/agents/AgentBase.py:16-74, 239-297``).
+The class name contains "PPO" because ``Config.get_if_off_policy`` classifies agents by name
+(``elegantrl/train/config.py:108-111``).
+
+What runs where
+    explore_env   built-in Pendulum env -> one fused persistent kernel (csrc/rollout.cu), which also produces
+                  V(s_t) and V(last_state); any other vec env -> one policy-step kernel per step
+                  (csrc/forward.cu) around the env's own ``step``
+    update_net    values (only if not already produced by the fused rollout) -> GAE reverse scan (csrc/gae.cu)
+                  -> ``update_times`` fused minibatch kernels (csrc/update.cu); one D2H copy of 3 floats
+PyTorch here is plumbing only: device memory, streams, ``torch.distributed``.  There is no fallback: without
+``libb200rl.so`` or without a CUDA device the agent raises.
+"""
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch as th
+from torch import nn
+
+from .. import _lib
+from .nets import ActorPPO, CriticPPO
+
+TEN = th.Tensor
+
+
+def _linears(module: nn.Module):
+    return [m for m in module.net if isinstance(m, nn.Linear)]
+
+
+def _trainable(module: nn.Module):
+    """Trainable tensors in the engine's flat order: W0, b0, W1, b1, ..., action_std_log."""
+    out = []
+    for layer in _linears(module):
+        out += [layer.weight, layer.bias]
+    if hasattr(module, "action_std_log"):
+        out.append(module.action_std_log)
+    return out
+
+
+class AgentPPO:
+    """PPO + GAE with the reference's arithmetic (incl. its quirks), B200-native engine."""
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int, gpu_id: int = 0, args=None):
+        if args is None:
+            from ..config import Config
+            args = Config()
+        # ---- fields of AgentBase.__init__ (reference AgentBase.py:27-68)
+        self.if_discrete = getattr(args, "if_discrete", False)
+        self.if_off_policy = False
+        self.net_dims = list(net_dims)
+        self.state_dim = int(state_dim)
+        self.action_dim = int(action_dim)
+        self.gamma = args.gamma
+        self.max_step = getattr(args, "max_step", 12345)
+        self.num_envs = getattr(args, "num_envs", None) or 1
+        self.batch_size = int(args.batch_size)
+        self.repeat_times = args.repeat_times
+        self.reward_scale = args.reward_scale
+        self.learning_rate = args.learning_rate
+        self.clip_grad_norm = args.clip_grad_norm
+        self.soft_update_tau = getattr(args, "soft_update_tau", 5e-3)
+        self.state_value_tau = getattr(args, "state_value_tau", 0)
+        self.explore_noise_std = getattr(args, "explore_noise_std", 0.05)
+        self.explore_rate = getattr(args, "explore_rate", 1.0)  # read by run.py:126 for every agent
+        self.last_state: Optional[TEN] = None
+        self.device = th.device(f"cuda:{gpu_id}" if (th.cuda.is_available() and gpu_id >= 0) else "cpu")
+        self.if_vec_env = self.num_envs > 1
+        assert not self.if_discrete, "this engine carries the continuous-action PPO path"
+
+        # ---- fields of AgentPPO.__init__ (reference AgentPPO.py:18-32)
+        activation = getattr(args, "activation", "gelu")
+        self.act = ActorPPO(self.net_dims, self.state_dim, self.action_dim, activation).to(self.device)
+        self.cri = CriticPPO(self.net_dims, self.state_dim, self.action_dim, activation).to(self.device)
+        self.act_target = self.cri_target = None
+        self.act_optimizer = th.optim.Adam(self.act.parameters(), self.learning_rate)
+        self.cri_optimizer = th.optim.Adam(self.cri.parameters(), self.learning_rate)
+        self.ratio_clip = getattr(args, "ratio_clip", 0.25)
+        self.lambda_gae_adv = getattr(args, "lambda_gae_adv", 0.95)
+        self.lambda_entropy = getattr(args, "lambda_entropy", 0.001)
+        self.if_use_v_trace = getattr(args, "if_use_v_trace", True)
+        self.save_attr_names = {"act", "act_target", "act_optimizer", "cri", "cri_target", "cri_optimizer"}
+
+        # ---- engine state (never pickled with act/cri: raw pointers are rebuilt on every call)
+        seed = getattr(args, "random_seed", None)
+        self.seed = int(max(0, gpu_id) if seed is None else seed)
+        self._update_draws = 0       # Philox offset of the minibatch index stream
+        self._policy_steps = 0       # Philox offset of the per-step policy kernel (external envs)
+        self._workspace: Optional[TEN] = None
+        self._value_cache = None     # (key, values [H, N], last_value [N]) produced by the fused rollout
+        self._dist_group = None      # set by enable_data_parallel()
+        self._rank, self._world = 0, 1
+        self.last_update_info = {}
+
+    # ------------------------------------------------------------------------------------ plumbing
+    def _require_engine(self):
+        if self.device.type != "cuda":
+            raise _lib.B200RLError("AgentPPO (B200 engine) needs a CUDA device; there is no CPU path "
+                                   "(the CPU oracle lives in oracle/ and is test infrastructure only)")
+        return _lib.load()
+
+    @staticmethod
+    def _check(t: TEN, name: str) -> TEN:
+        assert t.dtype == th.float32 and t.is_contiguous() and t.is_cuda, f"{name}: need contiguous fp32 CUDA tensor"
+        return t
+
+    def _net_desc(self, module: nn.Module) -> _lib.Net:
+        """C descriptor aliasing the module's parameter storages (rebuilt per call: cheap, always current)."""
+        linears = _linears(module)
+        assert 1 <= len(linears) <= _lib.MAX_LINEAR, "too many layers for the engine"
+        net = _lib.Net()
+        net.num_linear = len(linears)
+        net.activation = _lib.ACTIVATION_CODES[getattr(module, "activation", "gelu")]
+        net.dims[0] = linears[0].in_features
+        for i, layer in enumerate(linears):
+            net.dims[i + 1] = layer.out_features
+            net.weight[i] = self._check(layer.weight.data, "weight").data_ptr()
+            net.bias[i] = self._check(layer.bias.data, "bias").data_ptr()
+        if hasattr(module, "state_avg"):
+            net.state_avg = self._check(module.state_avg.data, "state_avg").data_ptr()
+            net.state_std = self._check(module.state_std.data, "state_std").data_ptr()
+        if hasattr(module, "action_std_log"):
+            net.action_std_log = self._check(module.action_std_log.data, "action_std_log").data_ptr()
+        return net
+
+    def _adam_desc(self, optimizer: th.optim.Adam, module: nn.Module) -> _lib.Adam:
+        """C descriptor aliasing the optimizer's exp_avg / exp_avg_sq tensors (created here if Adam has not
+        stepped yet, in exactly the form torch.optim.Adam itself would create them)."""
+        group = optimizer.param_groups[0]
+        assert not group.get("amsgrad", False) and group.get("weight_decay", 0) == 0 and not group.get("maximize", False)
+        adam = _lib.Adam()
+        adam.lr, adam.eps = group["lr"], group["eps"]
+        adam.beta1, adam.beta2 = group["betas"]
+        step = None
+        linears = _linears(module)
+        for i, layer in enumerate(linears):
+            for p, avg, sq in ((layer.weight, adam.exp_avg_w, adam.exp_avg_sq_w), (layer.bias, adam.exp_avg_b, adam.exp_avg_sq_b)):
+                st = self._adam_state(optimizer, p)
+                avg[i], sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                step = float(st["step"]) if step is None else step
+        if hasattr(module, "action_std_log"):
+            st = self._adam_state(optimizer, module.action_std_log)
+            adam.exp_avg_std, adam.exp_avg_sq_std = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+        adam.step = int(step or 0)
+        return adam
+
+    def _adam_state(self, optimizer, p):
+        st = optimizer.state[p]
+        if len(st) == 0:
+            st["step"] = th.tensor(0.0, dtype=th.float32)
+            st["exp_avg"] = th.zeros_like(p, memory_format=th.preserve_format)
+            st["exp_avg_sq"] = th.zeros_like(p, memory_format=th.preserve_format)
+        self._check(st["exp_avg"], "exp_avg")
+        self._check(st["exp_avg_sq"], "exp_avg_sq")
+        return st
+
+    @staticmethod
+    def _set_adam_step(optimizer, module, step: int):
+        for p in _trainable(module):
+            optimizer.state[p]["step"] = th.tensor(float(step), dtype=th.float32)
+
+    def _stream(self) -> int:
+        return th.cuda.current_stream(self.device).cuda_stream
+
+    def _get_workspace(self, act_desc, cri_desc) -> TEN:
+        lib = _lib.load()
+        need = lib.b200rl_workspace_bytes(C.byref(act_desc), C.byref(cri_desc))
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != self.device:
+            self._workspace = th.zeros(need, dtype=th.uint8, device=self.device)
+        return self._workspace
+
+    def enable_data_parallel(self, group=None):
+        """Shard envs over the ranks of a torch.distributed group: each rank rolls out / scans its own env slice;
+        per cycle one all-reduce of the advantage sums, per minibatch one all-reduce of the flat gradient
+        (SURVEY.md section 8(e)).  Replaces the reference's host-pipe trajectory all-gather (run.py:305-320)."""
+        import torch.distributed as dist
+        self._dist_group = group if group is not None else dist.group.WORLD
+        self._rank, self._world = dist.get_rank(self._dist_group), dist.get_world_size(self._dist_group)
+
+    # ------------------------------------------------------------------------------------- rollout
+    def explore_env(self, env, horizon_len: int) -> Tuple[TEN, TEN, TEN, TEN, TEN, TEN]:
+        """Reference AgentBase.explore_env dispatch (AgentBase.py:70-74) + AgentPPO._explore_vec_env /
+        _explore_one_env (AgentPPO.py:34-129).  Returns (states, actions, logprobs, rewards, undones, unmasks)."""
+        self._require_engine()
+        if getattr(env, "env_kind", None) == "pendulum" and self._fused_rollout_ok(env):
+            return self._explore_fused_pendulum(env, horizon_len)
+        if self.if_vec_env:
+            return self._explore_vec_env(env, horizon_len)
+        return self._explore_one_env(env, horizon_len)
+
+    def _fused_rollout_ok(self, env) -> bool:
+        return (env.device == self.device and self.state_dim == 3 and self.action_dim == 1
+                and tuple(self.net_dims) in ((64, 64), (128, 64)) and env.num_envs == self.num_envs)
+
+    def _explore_fused_pendulum(self, env, horizon_len: int):
+        lib = _lib.load()
+        n, h, dev = env.num_envs, int(horizon_len), self.device
+        theta, theta_dot, cur_step = env.engine_state()
+        states = th.empty((h, n, 3), dtype=th.float32, device=dev)
+        actions = th.empty((h, n, 1), dtype=th.float32, device=dev)
+        logprobs = th.empty((h, n), dtype=th.float32, device=dev)
+        rewards = th.empty((h, n), dtype=th.float32, device=dev)
+        undones = th.empty((h, n), dtype=th.bool, device=dev)
+        unmasks = th.empty((h, n), dtype=th.bool, device=dev)
+        values = th.empty((h, n), dtype=th.float32, device=dev)
+        last_state = th.empty((n, 3), dtype=th.float32, device=dev)
+        last_value = th.empty((n,), dtype=th.float32, device=dev)
+        act_desc, cri_desc = self._net_desc(self.act), self._net_desc(self.cri)
+        eps = getattr(self, "_inject_eps", None)
+        reset_noise = getattr(self, "_inject_reset_noise", None)
+        args = _lib.RolloutArgs(
+            actor=C.pointer(act_desc), critic=C.pointer(cri_desc), num_envs=n, horizon_len=h, max_step=env.max_step,
+            reward_scale=float(self.reward_scale), theta=_lib.ptr(theta), theta_dot=_lib.ptr(theta_dot),
+            cur_step=_lib.ptr(cur_step), states=_lib.ptr(states), actions=_lib.ptr(actions), logprobs=_lib.ptr(logprobs),
+            rewards=_lib.ptr(rewards), undones=_lib.ptr(undones), unmasks=_lib.ptr(unmasks), values=_lib.ptr(values),
+            last_state=_lib.ptr(last_state), last_value=_lib.ptr(last_value), eps=_lib.ptr(eps),
+            reset_noise=_lib.ptr(reset_noise), seed=self.seed, step_offset=env.global_step,
+            env_offset=self._rank * n)
+        _lib.check(lib.b200rl_rollout_pendulum(C.byref(args), self._stream()), "rollout_pendulum")
+        env.global_step += h
+        self.last_state = last_state
+        self._value_cache = (self._cache_key(states), values, last_value)
+        return states, actions, logprobs, rewards, undones, unmasks
+
+    def _cache_key(self, states: TEN):
+        return states.data_ptr(), tuple(states.shape), id(self.cri), self.cri.net[0].weight.data_ptr()
+
+    def explore_action(self, state: TEN) -> Tuple[TEN, TEN]:
+        """ActorPPO.get_action through the engine (reference AgentPPO.py:131-133): (action, logprob)."""
+        action, logprob, _ = self._policy_step(state)
+        return action, logprob
+
+    def _policy_step(self, state: TEN, eps: Optional[TEN] = None):
+        """One engine exploration step: (action [rows, A] pre-tanh, logprob [rows], env_action = tanh(action))."""
+        lib = self._require_engine()
+        state = self._check(state.to(self.device, th.float32).contiguous(), "state")
+        rows = state.shape[0]
+        action = th.empty((rows, self.action_dim), dtype=th.float32, device=self.device)
+        env_action = th.empty_like(action)
+        logprob = th.empty((rows,), dtype=th.float32, device=self.device)
+        act_desc = self._net_desc(self.act)
+        _lib.check(lib.b200rl_policy_step(C.byref(act_desc), None, _lib.ptr(state), rows, _lib.ptr(eps), self.seed,
+                                          self._policy_steps, self._rank * rows, _lib.ptr(action), _lib.ptr(logprob),
+                                          _lib.ptr(env_action), None, self._stream()), "policy_step")
+        self._policy_steps += 1
+        return action, logprob, env_action
+
+    def _explore_vec_env(self, env, horizon_len: int):
+        """External tensor vec env: engine policy step + the env's own step(), per time step."""
+        n, h, dev = self.num_envs, int(horizon_len), self.device
+        states = th.empty((h, n, self.state_dim), dtype=th.float32, device=dev)
+        actions = th.empty((h, n, self.action_dim), dtype=th.float32, device=dev)
+        logprobs = th.empty((h, n), dtype=th.float32, device=dev)
+        rewards = th.empty((h, n), dtype=th.float32, device=dev)
+        terminals = th.empty((h, n), dtype=th.bool, device=dev)
+        truncates = th.empty((h, n), dtype=th.bool, device=dev)
+        state = self.last_state.to(dev)
+        for t in range(h):
+            action, logprob, env_action = self._policy_step(state)
+            states[t], actions[t], logprobs[t] = state, action, logprob
+            state, reward, terminal, truncate, _ = env.step(env_action)
+            state = state.to(dev)
+            rewards[t], terminals[t], truncates[t] = reward, terminal, truncate
+        self.last_state = state
+        rewards *= self.reward_scale
+        self._value_cache = None
+        return states, actions, logprobs, rewards, th.logical_not(terminals), th.logical_not(truncates)
+
+    def _explore_one_env(self, env, horizon_len: int):
+        """Single gym-style env with numpy I/O (reference AgentPPO.py:34-85); outputs shaped [H, 1, ...]."""
+        h, dev = int(horizon_len), self.device
+        states = th.empty((h, 1, self.state_dim), dtype=th.float32, device=dev)
+        actions = th.empty((h, 1, self.action_dim), dtype=th.float32, device=dev)
+        logprobs = th.empty((h, 1), dtype=th.float32, device=dev)
+        rewards = th.zeros((h, 1), dtype=th.float32)
+        terminals = th.zeros((h, 1), dtype=th.bool)
+        truncates = th.zeros((h, 1), dtype=th.bool)
+        state = self.last_state.to(dev)
+        for t in range(h):
+            action, logprob, env_action = self._policy_step(state)
+            states[t], actions[t], logprobs[t] = state, action, logprob
+            ary_state, reward, terminal, truncate, _ = env.step(env_action[0].cpu().numpy())
+            if terminal or truncate:
+                ary_state, _ = env.reset()
+            state = th.as_tensor(np.asarray(ary_state), dtype=th.float32, device=dev).reshape(1, self.state_dim)
+            rewards[t], terminals[t], truncates[t] = float(reward), bool(terminal), bool(truncate)
+        self.last_state = state
+        self._value_cache = None
+        return (states, actions, logprobs, (rewards * self.reward_scale).to(dev),
+                th.logical_not(terminals).to(dev), th.logical_not(truncates).to(dev))
+
+    # -------------------------------------------------------------------------------------- update
+    def get_values(self, states: TEN) -> TEN:
+        """critic(states) for [..., S] -> [...] (reference update_net values pass, AgentPPO.py:141-143)."""
+        lib = self._require_engine()
+        flat = self._check(states.reshape(-1, self.state_dim), "states")
+        out = th.empty((flat.shape[0],), dtype=th.float32, device=self.device)
+        cri_desc = self._net_desc(self.cri)
+        _lib.check(lib.b200rl_mlp_forward(C.byref(cri_desc), _lib.ptr(flat), flat.shape[0], _lib.ptr(out), 0, self._stream()),
+                   "mlp_forward")
+        return out.reshape(states.shape[:-1])
+
+    def get_advantages(self, states: TEN, rewards: TEN, undones: TEN, unmasks: TEN, values: TEN,
+                       last_value: Optional[TEN] = None):
+        """Reference AgentPPO.get_advantages (AgentPPO.py:207-232); mutates rewards / undones in place like it.
+        Returns (advantages, reward_sums, stat_sums) -- the reduction inputs of the normalisation come for free."""
+        lib = self._require_engine()
+        h, n = rewards.shape
+        if last_value is None:
+            last_value = self.get_values(self.last_state.to(self.device))
+        advantages = th.empty_like(values)
+        reward_sums = th.empty_like(values)
+        stat_sums = th.empty(4, dtype=th.float64, device=self.device)
+        assert undones.dtype == th.bool and unmasks.dtype == th.bool
+        _lib.check(lib.b200rl_gae(_lib.ptr(self._check(rewards, "rewards")), _lib.ptr(undones), _lib.ptr(unmasks),
+                                  _lib.ptr(self._check(values, "values")), _lib.ptr(self._check(last_value, "last_value")),
+                                  h, n, float(self.gamma), float(self.lambda_gae_adv), int(bool(self.if_use_v_trace)),
+                                  self._rank * n, _lib.ptr(advantages), _lib.ptr(reward_sums), _lib.ptr(stat_sums),
+                                  self._stream()), "gae")
+        return advantages, reward_sums, stat_sums
+
+    def update_net(self, buffer) -> Tuple[float, float, float]:
+        """Reference AgentPPO.update_net (AgentPPO.py:135-171): returns (obj_critic, obj_actor, obj_entropy)
+        averaged over ``update_times = int(H * repeat_times / batch_size)`` minibatch updates."""
+        obj_critic, obj_actor, obj_entropy = self.update_net_device(buffer).tolist()  # the one D2H copy of the cycle
+        return obj_critic, obj_actor, obj_entropy
+
+    def update_net_device(self, buffer) -> TEN:
+        """``update_net`` without the host synchronisation: the three scalars stay in a device tensor."""
+        lib = self._require_engine()
+        states, actions, logprobs, rewards, undones, unmasks = buffer
+        h, n = states.shape[0], states.shape[1]
+        dev = self.device
+        states = self._check(states, "states")
+        actions = self._check(actions.reshape(h, n, self.action_dim), "actions")
+
+        # values: reuse what the fused rollout already computed with this very critic
+        cache = self._value_cache
+        if cache is not None and cache[0] == self._cache_key(states):
+            values, last_value = cache[1], cache[2]
+        else:
+            values = self.get_values(states)
+            last_value = None
+        self._value_cache = None
+        advantages, reward_sums, stat_sums = self.get_advantages(states, rewards, undones, unmasks, values, last_value)
+
+        n_global = n * self._world
+        if self._world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(stat_sums, group=self._dist_group)
+        stats = th.empty(4, dtype=th.float32, device=dev)
+        _lib.check(lib.b200rl_adv_stats(_lib.ptr(stat_sums), h * n_global, ((h + 3) // 4) * ((n_global + 3) // 4),
+                                        _lib.ptr(stats), self._stream()), "adv_stats")
+
+        update_times = int(h * self.repeat_times / self.batch_size)
+        assert update_times >= 1
+        act_desc, cri_desc = self._net_desc(self.act), self._net_desc(self.cri)
+        act_adam, cri_adam = self._adam_desc(self.act_optimizer, self.act), self._adam_desc(self.cri_optimizer, self.cri)
+        workspace = self._get_workspace(act_desc, cri_desc)
+        tb = _lib.TrainBuffer(states=_lib.ptr(states), actions=_lib.ptr(actions), unmasks=_lib.ptr(unmasks),
+                              logprobs=_lib.ptr(self._check(logprobs, "logprobs")), advantages=_lib.ptr(advantages),
+                              reward_sums=_lib.ptr(reward_sums), adv_stats=_lib.ptr(stats), horizon_len=h, num_envs=n)
+        hp = _lib.PPOHyper(ratio_clip=float(self.ratio_clip), lambda_entropy=float(self.lambda_entropy),
+                           clip_grad_norm=float(self.clip_grad_norm or 0.0))
+        out = th.empty(3, dtype=th.float32, device=dev)
+        ids = getattr(self, "_inject_ids", None)
+        if self._world == 1:
+            _lib.check(lib.b200rl_ppo_update(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam),
+                                             C.byref(tb), C.byref(hp), self.batch_size, update_times, _lib.ptr(ids),
+                                             self.seed, self._update_draws, _lib.ptr(out), _lib.ptr(workspace),
+                                             workspace.numel(), self._stream()), "ppo_update")
+        else:
+            self._update_sharded(lib, act_desc, cri_desc, act_adam, cri_adam, tb, hp, update_times, ids, out, workspace)
+        self._update_draws += update_times
+        self._set_adam_step(self.act_optimizer, self.act, act_adam.step)
+        self._set_adam_step(self.cri_optimizer, self.cri, cri_adam.step)
+        self.last_update_info = dict(update_times=update_times, advantages=advantages, reward_sums=reward_sums,
+                                     values=values, adv_stats=stats)
+        return out
+
+    def _update_sharded(self, lib, act_desc, cri_desc, act_adam, cri_adam, tb, hp, update_times, ids, out, workspace):
+        """Env-sharded minibatches: local gradient sums -> one NCCL all-reduce of the flat buffer -> clip + Adam
+        replicated on every rank (identical parameters everywhere without a broadcast)."""
+        import torch.distributed as dist
+        assert self.batch_size % self._world == 0, "batch_size must divide over the ranks"
+        local_batch = self.batch_size // self._world
+        grad_numel = lib.b200rl_grad_numel(C.byref(act_desc), C.byref(cri_desc))
+        grad_off = lib.b200rl_workspace_grad_offset()
+        flat_grads = workspace[grad_off:grad_off + 4 * grad_numel].view(th.float32)
+        loss_sums = th.zeros(4, dtype=th.float64, device=self.device)
+        seed = self.seed + 0x9E3779B9 * (self._rank + 1)  # independent index streams per shard
+        for u in range(update_times):
+            ids_u = ids[u] if ids is not None else None
+            _lib.check(lib.b200rl_ppo_grads(C.byref(act_desc), C.byref(cri_desc), C.byref(tb), C.byref(hp), local_batch,
+                                            self.batch_size, _lib.ptr(ids_u), seed, self._update_draws + u,
+                                            _lib.ptr(loss_sums), _lib.ptr(workspace), workspace.numel(), self._stream()),
+                       "ppo_grads")
+            dist.all_reduce(flat_grads, group=self._dist_group)
+            _lib.check(lib.b200rl_ppo_apply(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam),
+                                            C.byref(hp), _lib.ptr(workspace), workspace.numel(), self._stream()), "ppo_apply")
+        dist.all_reduce(loss_sums, group=self._dist_group)
+        _lib.check(lib.b200rl_loss_means(_lib.ptr(loss_sums), update_times, _lib.ptr(out), self._stream()), "loss_means")
+
+    # ------------------------------------------------------------------------------ checkpointing
+    def save_or_load_agent(self, cwd: str, if_save: bool):
+        """Whole-object ``th.save`` / ``th.load`` of act, cri and their optimizers, file names as the reference
+        (AgentBase.py:280-297)."""
+        for attr_name in sorted(self.save_attr_names):
+            obj = getattr(self, attr_name)
+            if obj is None:
+                continue
+            file_path = f"{cwd}/{attr_name}.pth"
+            if if_save:
+                th.save(obj, file_path)
+            elif os.path.isfile(file_path):
+                setattr(self, attr_name, th.load(file_path, map_location=self.device, weights_only=False))
+        if not if_save:
+            # a separately pickled optimizer refers to its own parameter copies (reference quirk): re-attach its
+            # state, by position, to an optimizer over the loaded modules so that training continues correctly
+            for opt_name, module in (("act_optimizer", self.act), ("cri_optimizer", self.cri)):
+                loaded = getattr(self, opt_name)
+                fresh = th.optim.Adam(module.parameters(), self.learning_rate)
+                for p_old, p_new in zip(loaded.param_groups[0]["params"], fresh.param_groups[0]["params"]):
+                    if p_old in loaded.state and len(loaded.state[p_old]):
+                        fresh.state[p_new] = {k: (v.to(p_new.device) if k != "step" and th.is_tensor(v) else v)
+                                              for k, v in loaded.state[p_old].items()}
+                setattr(self, opt_name, fresh)
+        self._value_cache = None

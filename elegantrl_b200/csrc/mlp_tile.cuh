@@ -1,0 +1,104 @@
+// Generic (runtime-dims) MLP tile routines on CUDA cores, shared by forward.cu and update.cu.
+//
+// A CTA owns a tile of TB samples.  Activations live in shared memory feature-major, X[k][b], so that the 32
+// lanes of a warp read consecutive samples of one feature row (conflict-free LDS.128) in the forward and
+// data-gradient GEMMs.  The weight-gradient GEMM (dW[j][k] = sum_b dZ[j][b] * X[k][b]) instead has lanes on
+// different feature rows at the same sample chunk; to keep that conflict-free too, the 16-byte sample chunk c
+// of row r is stored at chunk (c ^ (r/4)) -- an XOR swizzle keyed by the row's 4-row group.
+#pragma once
+#include "common.cuh"
+
+template <int TB>
+struct SmemTile {
+    static constexpr int kChunks = TB / 4;
+    // float offset of the 4-sample chunk c of feature row r
+    static DEV int chunk(int r, int c) { return r * TB + (((c ^ (r >> 2)) & (kChunks - 1)) << 2); }
+    static DEV int elem(int r, int b) { return chunk(r, b >> 2) + (b & 3); }
+};
+
+DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Load TB rows of x [rows, S] (row-major) starting at row0 into Xs[S][TB], applying state_norm
+// (reference AgentPPO.py:360-361): (s - avg) / (std + 1e-4).  Rows past the end are zero.
+template <int TB, int NT>
+DEV void load_state_tile(const b200rl_net& net, const float* __restrict__ x, int64_t rows, int64_t row0, float* Xs) {
+    const int S = net.dims[0];
+    for (int idx = threadIdx.x; idx < TB * S; idx += NT) {
+        int b = idx / S, k = idx - b * S;
+        int64_t row = row0 + b;
+        float v = 0.0f;
+        if (row < rows) {
+            v = x[row * S + k];
+            if (net.state_avg) v = (v - net.state_avg[k]) / (net.state_std[k] + 1e-4f);
+        }
+        Xs[SmemTile<TB>::elem(k, b)] = v;
+    }
+}
+
+// Ys[j][b] = act(sum_k W[j][k] * Xs[k][b] + bias[j]); optionally Gs[j][b] = act'(pre-activation).
+// Thread tile: 4 samples x 4 outputs.  W is read through the read-only path (L1-resident: a few KB per layer).
+template <int TB, int NT>
+DEV void linear_forward(const float* __restrict__ W, const float* __restrict__ bias, int K, int J, const float* Xs,
+                        float* Ys, float* Gs, int act, bool apply_act) {
+    constexpr int NSG = TB / 4, NOL = NT / NSG;
+    using T = SmemTile<TB>;
+    const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
+    const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int j0 = ol * 4; j0 < J; j0 += NOL * 4) {
+        float acc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            float bv = (j0 + jj < J) ? __ldg(bias + j0 + jj) : 0.0f;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc[jj][s] = bv;
+        }
+        if (vec) {
+            for (int k = 0; k < K; k += 4) {
+                float4 xv[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) xv[kk] = ld4(Xs + T::chunk(k + kk, sg));
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (j0 + jj < J) {
+                        float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)(j0 + jj) * K + k));
+                        acc[jj][0] = fmaf(w.x, xv[0].x, acc[jj][0]); acc[jj][1] = fmaf(w.x, xv[0].y, acc[jj][1]);
+                        acc[jj][2] = fmaf(w.x, xv[0].z, acc[jj][2]); acc[jj][3] = fmaf(w.x, xv[0].w, acc[jj][3]);
+                        acc[jj][0] = fmaf(w.y, xv[1].x, acc[jj][0]); acc[jj][1] = fmaf(w.y, xv[1].y, acc[jj][1]);
+                        acc[jj][2] = fmaf(w.y, xv[1].z, acc[jj][2]); acc[jj][3] = fmaf(w.y, xv[1].w, acc[jj][3]);
+                        acc[jj][0] = fmaf(w.z, xv[2].x, acc[jj][0]); acc[jj][1] = fmaf(w.z, xv[2].y, acc[jj][1]);
+                        acc[jj][2] = fmaf(w.z, xv[2].z, acc[jj][2]); acc[jj][3] = fmaf(w.z, xv[2].w, acc[jj][3]);
+                        acc[jj][0] = fmaf(w.w, xv[3].x, acc[jj][0]); acc[jj][1] = fmaf(w.w, xv[3].y, acc[jj][1]);
+                        acc[jj][2] = fmaf(w.w, xv[3].z, acc[jj][2]); acc[jj][3] = fmaf(w.w, xv[3].w, acc[jj][3]);
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < K; ++k) {
+                float4 xv = ld4(Xs + T::chunk(k, sg));
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (j0 + jj < J) {
+                        float w = __ldg(W + (size_t)(j0 + jj) * K + k);
+                        acc[jj][0] = fmaf(w, xv.x, acc[jj][0]); acc[jj][1] = fmaf(w, xv.y, acc[jj][1]);
+                        acc[jj][2] = fmaf(w, xv.z, acc[jj][2]); acc[jj][3] = fmaf(w, xv.w, acc[jj][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            if (j0 + jj < J) {
+                float4 y = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+                if (apply_act) {
+                    if (Gs) {
+                        st4(Gs + T::chunk(j0 + jj, sg), make_float4(act_grad_rt(y.x, act), act_grad_rt(y.y, act),
+                                                                    act_grad_rt(y.z, act), act_grad_rt(y.w, act)));
+                    }
+                    y = make_float4(act_fn_rt(y.x, act), act_fn_rt(y.y, act), act_fn_rt(y.z, act), act_fn_rt(y.w, act));
+                }
+                st4(Ys + T::chunk(j0 + jj, sg), y);
+            }
+        }
+    }
+}

@@ -1,0 +1,488 @@
+// PPO minibatch update (any depth / widths): gather -> critic & actor forward -> losses -> backward ->
+// per-net grad-norm clip -> Adam, one kernel launch per minibatch, no host synchronisation.
+//
+// Replaces reference AgentPPO.update_objectives (elegantrl/agents/AgentPPO.py:173-205) and
+// AgentBase.optimizer_backward (elegantrl/agents/AgentBase.py:239-248: zero_grad, backward,
+// clip_grad_norm_, Adam.step -- per net, hence two independent norms).
+//
+// Grid: one CTA per tile of 32 sampled transitions.  Each CTA accumulates its weight-gradient tile products
+// into the flat fp32 gradient buffer of the workspace with RED.ADD; the CTA that takes the last ticket
+// ("last block done") computes the two grad norms, clips, applies Adam in place on the caller's parameter /
+// moment tensors, and re-zeroes the buffer for the next minibatch.  Sharded (multi-GPU) callers stop after the
+// gradient phase (b200rl_ppo_grads), all-reduce the flat buffer, then run b200rl_ppo_apply.
+#include "mlp_tile.cuh"
+
+namespace {
+
+constexpr int kUpdThreads = 256;
+constexpr int UTB = 32;  // samples per CTA
+using UT = SmemTile<UTB>;
+
+struct AdamScalars {
+    float step_size;  // lr / (1 - beta1^t)
+    float bc2_sqrt;   // sqrt(1 - beta2^t)
+};
+
+struct UpdateArgs {
+    b200rl_net net[2];  // 0 = actor, 1 = critic
+    b200rl_adam opt[2];
+    AdamScalars adam[2];
+    b200rl_train_buffer buf;
+    b200rl_ppo_hyper hp;
+    const int64_t* ids;  // [local_batch] or nullptr
+    uint64_t seed, draw;
+    int local_batch, global_batch;
+    float* grads;              // flat: actor tensors then critic tensors
+    int grad_off[2];           // float offset of each net's first tensor
+    int grad_numel[2];
+    WorkspaceHeader* hdr;
+    double* loss_sums;         // [3] obj_critic, obj_surrogate, obj_entropy (sums over updates)
+    int fused_apply;
+    int smem_scalar_off;       // float offset of the per-sample scalar block in dynamic smem
+    int maxdim;
+};
+
+// dW[j][k] += sum_b dZ[j][b] * X[k][b];  db[j] += sum_b dZ[j][b]      (RED.ADD into the flat buffer)
+DEV void weight_grad(const float* dZ, const float* X, int J, int K, float* gW, float* gb) {
+    const int JT = (J + 3) >> 2, KT = (K + 3) >> 2;
+    for (int tile = threadIdx.x; tile < JT * KT; tile += kUpdThreads) {
+        const int jt = tile / KT, kt = tile - jt * KT;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+#pragma unroll 2
+        for (int c = 0; c < UT::kChunks; ++c) {
+            float4 dz[4], xv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                dz[jj] = (4 * jt + jj < J) ? ld4(dZ + UT::chunk(4 * jt + jj, c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                xv[kk] = (4 * kt + kk < K) ? ld4(X + UT::chunk(4 * kt + kk, c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    acc[jj][kk] = fmaf(dz[jj].x, xv[kk].x, acc[jj][kk]);
+                    acc[jj][kk] = fmaf(dz[jj].y, xv[kk].y, acc[jj][kk]);
+                    acc[jj][kk] = fmaf(dz[jj].z, xv[kk].z, acc[jj][kk]);
+                    acc[jj][kk] = fmaf(dz[jj].w, xv[kk].w, acc[jj][kk]);
+                }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                if (4 * jt + jj < J && 4 * kt + kk < K) atomicAdd(gW + (size_t)(4 * jt + jj) * K + 4 * kt + kk, acc[jj][kk]);
+    }
+    for (int j = threadIdx.x; j < J; j += kUpdThreads) {
+        float s = 0.0f;
+        for (int c = 0; c < UT::kChunks; ++c) {
+            float4 v = ld4(dZ + UT::chunk(j, c));
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+        atomicAdd(gb + j, s);
+    }
+}
+
+// dZprev[k][b] = (sum_j W[j][k] * dZ[j][b]) * G[k][b]
+DEV void data_grad(const float* W, const float* dZ, const float* G, float* dZprev, int J, int K) {
+    constexpr int NSG = UTB / 4, NOL = kUpdThreads / NSG;
+    const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
+    const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int k0 = ol * 4; k0 < K; k0 += NOL * 4) {
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+        for (int j = 0; j < J; ++j) {
+            float4 dz = ld4(dZ + UT::chunk(j, sg));
+            float w[4];
+            if (vec) {
+                float4 w4 = *reinterpret_cast<const float4*>(W + (size_t)j * K + k0);
+                w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) w[kk] = (k0 + kk < K) ? W[(size_t)j * K + k0 + kk] : 0.0f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                acc[kk][0] = fmaf(w[kk], dz.x, acc[kk][0]); acc[kk][1] = fmaf(w[kk], dz.y, acc[kk][1]);
+                acc[kk][2] = fmaf(w[kk], dz.z, acc[kk][2]); acc[kk][3] = fmaf(w[kk], dz.w, acc[kk][3]);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            if (k0 + kk < K) {
+                float4 g = ld4(G + UT::chunk(k0 + kk, sg));
+                st4(dZprev + UT::chunk(k0 + kk, sg),
+                    make_float4(acc[kk][0] * g.x, acc[kk][1] * g.y, acc[kk][2] * g.z, acc[kk][3] * g.w));
+            }
+        }
+    }
+}
+
+DEV float block_sum(float v, float* red /*[32]*/) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kUpdThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+// clip_grad_norm_ + Adam.step for one net, executed by one whole CTA.
+DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
+                   float clip_grad_norm, float* red) {
+    float ss = 0.0f;
+    for (int i = threadIdx.x; i < numel; i += kUpdThreads) {
+        float v = __ldcg(g + i);
+        ss = fmaf(v, v, ss);
+    }
+    float total_norm = sqrtf(block_sum(ss, red));
+    float coef = 1.0f;
+    if (clip_grad_norm > 0.0f) coef = fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f);
+    const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps;
+    int off = 0;
+    const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
+    for (int ti = 0; ti < n_tensors; ++ti) {
+        float *p, *m, *v;
+        int count;
+        const int l = ti >> 1;
+        if (ti == 2 * net.num_linear) {
+            p = net.action_std_log; m = opt.exp_avg_std; v = opt.exp_avg_sq_std; count = net.dims[net.num_linear];
+        } else if ((ti & 1) == 0) {
+            p = net.weight[l]; m = opt.exp_avg_w[l]; v = opt.exp_avg_sq_w[l]; count = net.dims[l + 1] * net.dims[l];
+        } else {
+            p = net.bias[l]; m = opt.exp_avg_b[l]; v = opt.exp_avg_sq_b[l]; count = net.dims[l + 1];
+        }
+        for (int i = threadIdx.x; i < count; i += kUpdThreads) {
+            float gi = __ldcg(g + off + i) * coef;
+            float mi = m[i], vi = v[i];
+            mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), 1.0f - b1));                 // exp_avg.lerp_(grad, 1 - beta1)
+            vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(__fmul_rn(1.0f - b2, gi), gi));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
+            float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), as.bc2_sqrt), eps);
+            p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(-as.step_size, mi), denom));      // addcdiv_(exp_avg, denom, -step_size)
+            m[i] = mi; v[i] = vi;
+        }
+        off += count;
+    }
+}
+
+__global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_constant__ UpdateArgs A) {
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
+    __shared__ float red[32];
+    __shared__ int64_t s_tn[UTB];  // t * N + n of each sample
+    __shared__ int s_last;
+
+    const int H = A.buf.horizon_len, N = A.buf.num_envs;
+    const int slot0 = blockIdx.x * UTB;
+    float* sc = smem + A.smem_scalar_off;  // per-sample scalars
+    float* s_unmask = sc, *s_logp = sc + UTB, *s_adv = sc + 2 * UTB, *s_rsum = sc + 3 * UTB, *s_act = sc + 4 * UTB;
+
+    // ---- gather (reference :178-187): ids -> (t = id % H, n = id / H)
+    if (threadIdx.x < UTB) {
+        const int b = threadIdx.x, slot = slot0 + b;
+        int64_t tn = -1;
+        float um = 0.f, lp = 0.f, adv = 0.f, rs = 0.f;
+        if (slot < A.local_batch) {
+            int64_t id = A.ids ? A.ids[slot] : sample_index(A.seed, A.draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+            int64_t t = id % H, n = id / H;
+            tn = t * N + n;
+            um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
+            lp = A.buf.logprobs[tn];
+            adv = A.buf.advantages[tn];
+            if (A.buf.adv_stats) adv = (adv - A.buf.adv_stats[0]) / (A.buf.adv_stats[1] + 1e-5f);
+            rs = A.buf.reward_sums[tn];
+        }
+        s_tn[b] = tn; s_unmask[b] = um; s_logp[b] = lp; s_adv[b] = adv; s_rsum[b] = rs;
+    }
+    __syncthreads();
+    {
+        const int Adim = A.net[0].dims[A.net[0].num_linear];
+        for (int idx = threadIdx.x; idx < UTB * Adim; idx += kUpdThreads) {
+            int b = idx / Adim, a = idx - b * Adim;
+            s_act[a * UTB + b] = s_tn[b] >= 0 ? A.buf.actions[s_tn[b] * Adim + a] : 0.0f;
+        }
+    }
+    const float inv_bsz = 1.0f / (float)A.global_batch;
+    float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;  // valid in threads < UTB
+
+    // ---- critic (net 1) then actor (net 0): the nets are disjoint, order is immaterial (reference :189-204)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ni = 1 - pass;
+        const b200rl_net& net = A.net[ni];
+        const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
+        // smem map: X[0..L-1] (inputs of each Linear), G[1..L-1] (act' at each hidden layer), dzA, dzB
+        int xoff[B200RL_MAX_LINEAR + 1], goff[B200RL_MAX_LINEAR + 1];
+        int off = 0;
+        for (int l = 0; l < L; ++l) { xoff[l] = off; off += net.dims[l] * UTB; }
+        for (int l = 1; l < L; ++l) { goff[l] = off; off += net.dims[l] * UTB; }
+        float* dzA = smem + off;
+        float* dzB = dzA + A.maxdim * UTB;
+
+        // gather + state_norm into X[0]
+        for (int idx = threadIdx.x; idx < UTB * S; idx += kUpdThreads) {
+            int b = idx / S, k = idx - b * S;
+            float v = 0.0f;
+            if (s_tn[b] >= 0) {
+                v = A.buf.states[s_tn[b] * S + k];
+                if (net.state_avg) v = (v - net.state_avg[k]) / (net.state_std[k] + 1e-4f);
+            }
+            smem[xoff[0] + UT::elem(k, b)] = v;
+        }
+        __syncthreads();
+        // forward, keeping every layer input and act'
+        for (int l = 0; l < L; ++l) {
+            const bool hidden = l < L - 1;
+            linear_forward<UTB, kUpdThreads>(net.weight[l], net.bias[l], net.dims[l], net.dims[l + 1], smem + xoff[l],
+                                             hidden ? smem + xoff[l + 1] : dzA, hidden ? smem + goff[l + 1] : nullptr,
+                                             net.activation, hidden);
+            __syncthreads();
+        }
+        // loss and d loss / d output, in place in dzA
+        float* g = A.grads + A.grad_off[ni];
+        if (threadIdx.x < UTB) {
+            const int b = threadIdx.x;
+            const bool valid = s_tn[b] >= 0;
+            const float um = s_unmask[b];
+            if (ni == 1) {
+                // obj_critic = mean(MSE(V(s), reward_sum) * unmask)          (:189-190)
+                float err = dzA[UT::elem(0, b)] - s_rsum[b];
+                loss_c = valid ? err * err * um : 0.0f;
+                dzA[UT::elem(0, b)] = valid ? 2.0f * err * um * inv_bsz : 0.0f;
+            } else {
+                // new_logprob, ratio, "clip" factor, entropy                 (:193-203)
+                float logp = 0.0f, ent = 0.0f;
+                for (int a = 0; a < OUT; ++a) {
+                    float sd = expf(net.action_std_log[a]);
+                    float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
+                    float lsd = logf(sd);
+                    logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
+                    ent += 0.5f + kLogSqrt2Pi + lsd;  // 0.5 + 0.5 log(2 pi) + log(scale)
+                }
+                float ratio = expf(logp - s_logp[b]);
+                float adv = s_adv[b];
+                float kappa = adv > 0.0f ? 1.0f - A.hp.ratio_clip : 1.0f + A.hp.ratio_clip;
+                float surr = adv * ratio * kappa;
+                loss_s = valid ? surr * um : 0.0f;
+                loss_e = valid ? ent * um : 0.0f;
+                // loss = -(obj_surrogate - lambda_entropy * obj_entropy)
+                float gl = valid ? -(surr * um) * inv_bsz : 0.0f;
+                for (int a = 0; a < OUT; ++a) {
+                    float sd = expf(net.action_std_log[a]);
+                    float var = sd * sd;
+                    float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
+                    dzA[UT::elem(a, b)] = gl * diff / var;
+                    float dstd = gl * (diff * diff / var - 1.0f) + (valid ? A.hp.lambda_entropy * um * inv_bsz : 0.0f);
+                    dstd = warp_sum(dstd);  // UTB == 32: exactly warp 0
+                    if (b == 0) atomicAdd(g + A.grad_numel[0] - OUT + a, dstd);
+                }
+            }
+        }
+        __syncthreads();
+        // backward
+        float* dz = dzA;
+        float* dzn = dzB;
+        int goff_w = 0;  // float offset of W_l inside this net's flat gradient
+        int woff[B200RL_MAX_LINEAR];
+        for (int l = 0; l < L; ++l) { woff[l] = goff_w; goff_w += net.dims[l + 1] * net.dims[l] + net.dims[l + 1]; }
+        for (int l = L - 1; l >= 0; --l) {
+            const int J = net.dims[l + 1], K = net.dims[l];
+            weight_grad(dz, smem + xoff[l], J, K, g + woff[l], g + woff[l] + J * K);
+            if (l > 0) data_grad(net.weight[l], dz, smem + goff[l], dzn, J, K);
+            __syncthreads();
+            float* t = dz; dz = dzn; dzn = t;
+        }
+    }
+
+    // ---- loss sums (means over the global batch) -> double accumulators
+    if (threadIdx.x < 32) {
+        float c = warp_sum(loss_c), s = warp_sum(loss_s), e = warp_sum(loss_e);
+        if (threadIdx.x == 0) {
+            atomicAdd(A.loss_sums + 0, (double)(c * inv_bsz));
+            atomicAdd(A.loss_sums + 1, (double)(s * inv_bsz));
+            atomicAdd(A.loss_sums + 2, (double)(e * inv_bsz));
+        }
+    }
+    if (!A.fused_apply) return;
+
+    // ---- last block done: clip + Adam for both nets, then re-zero the gradient buffer
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&A.hdr->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int ni = 0; ni < 2; ++ni)
+        apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+    __syncthreads();
+    for (int i = threadIdx.x; i < A.grad_numel[0] + A.grad_numel[1]; i += kUpdThreads) A.grads[i] = 0.0f;
+    if (threadIdx.x == 0) A.hdr->ticket = 0u;
+}
+
+__global__ void __launch_bounds__(kUpdThreads) ppo_apply_kernel(const __grid_constant__ UpdateArgs A) {
+    __shared__ float red[32];
+    for (int ni = 0; ni < 2; ++ni)
+        apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+}
+
+__global__ void loss_means_kernel(const double* loss_sums, double inv_updates, float* out) {
+    if (threadIdx.x < 3) out[threadIdx.x] = (float)(loss_sums[threadIdx.x] * inv_updates);
+}
+
+AdamScalars adam_scalars(const b200rl_adam* opt, int64_t step) {
+    // torch.optim.Adam (_single_tensor_adam): step_size = lr / (1 - beta1^t); sqrt(1 - beta2^t) -- in double
+    double bc1 = 1.0 - pow((double)opt->beta1, (double)step);
+    double bc2 = 1.0 - pow((double)opt->beta2, (double)step);
+    AdamScalars s;
+    s.step_size = (float)((double)opt->lr / bc1);
+    s.bc2_sqrt = (float)sqrt(bc2);
+    return s;
+}
+
+int fill_args(UpdateArgs& A, const b200rl_net* actor, const b200rl_net* critic, const b200rl_adam* actor_opt,
+              const b200rl_adam* critic_opt, const b200rl_train_buffer* buffer, const b200rl_ppo_hyper* hyper,
+              void* workspace, int64_t workspace_bytes, size_t* smem_bytes) {
+    if (int rc = b200rl_validate_net(actor, "ppo.actor", true)) return rc;
+    if (int rc = b200rl_validate_net(critic, "ppo.critic", false)) return rc;
+    B200RL_REQUIRE(hyper && workspace, "ppo: hyper/workspace is NULL");
+    B200RL_REQUIRE(critic->dims[critic->num_linear] == 1, "ppo: critic output dim must be 1");
+    B200RL_REQUIRE(actor->dims[0] == critic->dims[0], "ppo: actor/critic state_dim differ");
+    B200RL_REQUIRE(workspace_bytes >= b200rl_workspace_bytes(actor, critic), "ppo: workspace too small (%lld < %lld)",
+                   (long long)workspace_bytes, (long long)b200rl_workspace_bytes(actor, critic));
+    B200RL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "ppo: workspace must be 256-byte aligned");
+    A.net[0] = *actor; A.net[1] = *critic;
+    if (actor_opt) A.opt[0] = *actor_opt;
+    if (critic_opt) A.opt[1] = *critic_opt;
+    if (buffer) A.buf = *buffer;
+    A.hp = *hyper;
+    A.hdr = reinterpret_cast<WorkspaceHeader*>(workspace);
+    A.grads = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200RL_WS_HEADER_BYTES);
+    A.grad_numel[0] = (int)b200rl_net_numel(actor);
+    A.grad_numel[1] = (int)b200rl_net_numel(critic);
+    A.grad_off[0] = 0;
+    A.grad_off[1] = A.grad_numel[0];
+    // dynamic smem: max over nets of (sum of Linear input dims + sum of hidden dims) + 2 * maxdim, + scalars
+    int maxdim = 0, rows = 0;
+    for (int ni = 0; ni < 2; ++ni) {
+        const b200rl_net& n = A.net[ni];
+        int r = 0;
+        for (int l = 0; l < n.num_linear; ++l) r += n.dims[l];
+        for (int l = 1; l < n.num_linear; ++l) r += n.dims[l];
+        rows = r > rows ? r : rows;
+        int md = b200rl_net_maxdim(&n);
+        maxdim = md > maxdim ? md : maxdim;
+    }
+    A.maxdim = maxdim;
+    A.smem_scalar_off = (rows + 2 * maxdim) * UTB;
+    int scalars = (4 + actor->dims[actor->num_linear]) * UTB;
+    *smem_bytes = (size_t)(A.smem_scalar_off + scalars) * sizeof(float);
+    B200RL_REQUIRE(*smem_bytes <= 227 * 1024, "ppo: nets too wide for the update kernel (%zu B of shared memory needed)",
+                   *smem_bytes);
+    return 0;
+}
+
+int check_buffer(const b200rl_train_buffer* b) {
+    B200RL_REQUIRE(b && b->states && b->actions && b->unmasks && b->logprobs && b->advantages && b->reward_sums,
+                   "ppo: NULL training buffer field");
+    B200RL_REQUIRE(b->horizon_len >= 1 && b->num_envs >= 1, "ppo: horizon_len=%d num_envs=%d", b->horizon_len, b->num_envs);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt, b200rl_adam* critic_opt,
+                      const b200rl_train_buffer* buffer, const b200rl_ppo_hyper* hyper, int32_t batch_size,
+                      int32_t update_times, const int64_t* ids, uint64_t seed, uint64_t draw_offset, float* out_scalars,
+                      void* workspace, int64_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200RL_REQUIRE(actor_opt && critic_opt && out_scalars, "ppo_update: NULL optimizer / output");
+    B200RL_REQUIRE(batch_size >= 1 && update_times >= 1, "ppo_update: batch_size=%d update_times=%d", batch_size, update_times);
+    if (int rc = check_buffer(buffer)) return rc;
+    UpdateArgs A{};
+    size_t smem = 0;
+    if (int rc = fill_args(A, actor, critic, actor_opt, critic_opt, buffer, hyper, workspace, workspace_bytes, &smem)) return rc;
+    A.loss_sums = A.hdr->loss_sums;
+    A.fused_apply = 1;
+    A.local_batch = A.global_batch = batch_size;
+    A.seed = seed;
+    B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200RL_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)b200rl_workspace_bytes(actor, critic), stream));
+    const unsigned grid = (unsigned)((batch_size + UTB - 1) / UTB);
+    for (int u = 0; u < update_times; ++u) {
+        A.ids = ids ? ids + (size_t)u * batch_size : nullptr;
+        A.draw = draw_offset + (uint64_t)u;
+        A.adam[0] = adam_scalars(actor_opt, actor_opt->step + u + 1);
+        A.adam[1] = adam_scalars(critic_opt, critic_opt->step + u + 1);
+        ppo_grads_kernel<<<grid, kUpdThreads, smem, stream>>>(A);
+    }
+    B200RL_COUNT_LAUNCH(update_times + 1);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    loss_means_kernel<<<1, 32, 0, stream>>>(A.loss_sums, 1.0 / (double)update_times, out_scalars);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    actor_opt->step += update_times;
+    critic_opt->step += update_times;
+    return 0;
+}
+
+int b200rl_ppo_grads(const b200rl_net* actor, const b200rl_net* critic, const b200rl_train_buffer* buffer,
+                     const b200rl_ppo_hyper* hyper, int32_t local_batch, int32_t global_batch, const int64_t* ids,
+                     uint64_t seed, uint64_t draw_offset, double* loss_sums, void* workspace, int64_t workspace_bytes,
+                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200RL_REQUIRE(loss_sums, "ppo_grads: loss_sums is NULL");
+    B200RL_REQUIRE(local_batch >= 1 && global_batch >= local_batch, "ppo_grads: local_batch=%d global_batch=%d", local_batch,
+                   global_batch);
+    if (int rc = check_buffer(buffer)) return rc;
+    UpdateArgs A{};
+    size_t smem = 0;
+    if (int rc = fill_args(A, actor, critic, nullptr, nullptr, buffer, hyper, workspace, workspace_bytes, &smem)) return rc;
+    A.loss_sums = loss_sums;
+    A.fused_apply = 0;
+    A.local_batch = local_batch;
+    A.global_batch = global_batch;
+    A.ids = ids;
+    A.seed = seed;
+    A.draw = draw_offset;
+    B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200RL_CHECK_CUDA(cudaMemsetAsync(A.grads, 0, (size_t)(A.grad_numel[0] + A.grad_numel[1]) * sizeof(float), stream));
+    ppo_grads_kernel<<<(unsigned)((local_batch + UTB - 1) / UTB), kUpdThreads, smem, stream>>>(A);
+    B200RL_COUNT_LAUNCH(1);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b200rl_ppo_apply(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt, b200rl_adam* critic_opt,
+                     const b200rl_ppo_hyper* hyper, void* workspace, int64_t workspace_bytes, void* stream_) {
+    B200RL_REQUIRE(actor_opt && critic_opt, "ppo_apply: NULL optimizer");
+    UpdateArgs A{};
+    size_t smem = 0;
+    if (int rc = fill_args(A, actor, critic, actor_opt, critic_opt, nullptr, hyper, workspace, workspace_bytes, &smem)) return rc;
+    A.adam[0] = adam_scalars(actor_opt, actor_opt->step + 1);
+    A.adam[1] = adam_scalars(critic_opt, critic_opt->step + 1);
+    ppo_apply_kernel<<<1, kUpdThreads, 0, (cudaStream_t)stream_>>>(A);
+    B200RL_COUNT_LAUNCH(1);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    actor_opt->step += 1;
+    critic_opt->step += 1;
+    return 0;
+}
+
+int b200rl_loss_means(const double* loss_sums, int32_t update_times, float* out_scalars, void* stream) {
+    B200RL_REQUIRE(loss_sums && out_scalars && update_times >= 1, "loss_means: bad arguments");
+    loss_means_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_sums, 1.0 / (double)update_times, out_scalars);
+    B200RL_COUNT_LAUNCH(1);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

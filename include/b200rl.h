@@ -1,0 +1,192 @@
+/* libb200rl -- C ABI of the B200-native on-policy engine (rollout -> GAE -> PPO update).
+ *
+ * The reference (AI4Finance-Foundation/ElegantRL) has no FFI for this path: the boundary is the Python
+ * duck-typed Agent API.  This header is the C-ABI a binding for that boundary calls;
+ * each entry point names the reference function it replaces (paths relative to the reference checkout).
+ * The Python shim that mirrors the reference's `AgentPPO` on top of it is elegantrl_b200/agents/AgentPPO.py;
+ * the ctypes stub is elegantrl_b200/_lib.py (also shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless a comment says host
+ *  - all work is enqueued on the caller's CUDA stream (`stream` = cudaStream_t, may be NULL = default stream);
+ *    no entry point synchronises the device or allocates device memory
+ *  - scratch memory is a caller-provided `workspace` (size from b200rl_workspace_bytes)
+ *  - every entry point returns 0 on success, non-zero on failure; b200rl_last_error() gives the text of the
+ *    last failure on the calling thread.  One host thread per engine (the reference is single-threaded per
+ *    process).
+ *  - float = IEEE fp32; masks are 1-byte bools exactly as torch.bool tensors; indices are int64.
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200RL_API __attribute__((visibility("default")))
+#else
+#define B200RL_API
+#endif
+
+#define B200RL_MAX_LINEAR 8 /* nn.Linear layers per net = len(net_dims) + 1 */
+#define B200RL_ACT_GELU 0   /* nn.GELU(), exact erf form -- reference AgentBase.py:353-354 */
+#define B200RL_ACT_RELU 1   /* helloworld nets -- reference helloworld_PPO_single_file.py:172-212 */
+
+/* One MLP of the reference's `build_mlp` (elegantrl/agents/AgentBase.py:345-360) plus the state_norm
+ * statistics of ActorPPO / CriticPPO (elegantrl/agents/AgentPPO.py:357-361, 432-441).  Pointers alias the
+ * storages of the caller's nn.Parameter tensors: the engine reads and (in the update) writes them in place. */
+typedef struct b200rl_net {
+    int32_t num_linear;                   /* 1..B200RL_MAX_LINEAR */
+    int32_t activation;                   /* B200RL_ACT_* applied after every Linear but the last */
+    int32_t dims[B200RL_MAX_LINEAR + 1];  /* dims[0] = state_dim, dims[num_linear] = output dim */
+    int32_t reserved;
+    float* weight[B200RL_MAX_LINEAR];     /* [dims[l+1], dims[l]] row-major (nn.Linear.weight) */
+    float* bias[B200RL_MAX_LINEAR];       /* [dims[l+1]] */
+    const float* state_avg;               /* [dims[0]] or NULL: no state_norm at all (helloworld) */
+    const float* state_std;               /* [dims[0]]; normalised input = (s - avg) / (std + 1e-4) */
+    float* action_std_log;                /* actor: [action_dim] (ActorPPO.action_std_log); critic: NULL */
+} b200rl_net;
+
+/* torch.optim.Adam state of one net (reference AgentPPO.py:24-25; stepped by AgentBase.py:239-248), tensor
+ * order W0, b0, W1, b1, ..., action_std_log.  Pointers alias optimizer.state[p]['exp_avg' / 'exp_avg_sq']. */
+typedef struct b200rl_adam {
+    float* exp_avg_w[B200RL_MAX_LINEAR];
+    float* exp_avg_b[B200RL_MAX_LINEAR];
+    float* exp_avg_sq_w[B200RL_MAX_LINEAR];
+    float* exp_avg_sq_b[B200RL_MAX_LINEAR];
+    float* exp_avg_std;                   /* actor only, else NULL */
+    float* exp_avg_sq_std;
+    float lr, beta1, beta2, eps;
+    int64_t step;                         /* optimizer steps already taken; advanced by the engine (host field) */
+} b200rl_adam;
+
+/* Hyper-parameters of AgentPPO.update_objectives (reference AgentPPO.py:27-30, 189-204). */
+typedef struct b200rl_ppo_hyper {
+    float ratio_clip;                     /* AgentPPO.ratio_clip (0.25) */
+    float lambda_entropy;                 /* AgentPPO.lambda_entropy (0.001) */
+    float clip_grad_norm;                 /* Config.clip_grad_norm (3.0); <= 0 disables clipping */
+    int32_t reserved;
+} b200rl_ppo_hyper;
+
+/* The training buffer of AgentPPO.update_net after the GAE pass (reference AgentPPO.py:151):
+ * (states, actions, unmasks, logprobs, advantages, reward_sums), time-major [H, N, ...]. */
+typedef struct b200rl_train_buffer {
+    const float* states;                  /* [H, N, S] */
+    const float* actions;                 /* [H, N, A] */
+    const uint8_t* unmasks;               /* [H, N] bool */
+    const float* logprobs;                /* [H, N] */
+    const float* advantages;              /* [H, N] */
+    const float* reward_sums;             /* [H, N] */
+    const float* adv_stats;               /* [4] = {mean, std, ...} from b200rl_adv_stats: (adv - mean)/(std + 1e-5)
+                                             is applied at gather time; NULL when `advantages` is already
+                                             normalised (reference :149) */
+    int32_t horizon_len;                  /* H */
+    int32_t num_envs;                     /* N */
+} b200rl_train_buffer;
+
+/* Fused rollout on the built-in Pendulum-v1 vec env: replaces the Python loop of
+ * AgentPPO._explore_vec_env (reference AgentPPO.py:87-129) including ActorPPO.get_action (:368-376), the
+ * env.step call (:119) and -- when `critic` is given -- the values pass of update_net (:141-143). */
+typedef struct b200rl_rollout_args {
+    const b200rl_net* actor;              /* host pointer */
+    const b200rl_net* critic;             /* host pointer or NULL (then `values` is not written) */
+    int32_t num_envs;                     /* N (this rank's shard) */
+    int32_t horizon_len;                  /* H */
+    int32_t max_step;                     /* episode truncation length (200 for Pendulum-v1) */
+    float reward_scale;                   /* AgentBase.reward_scale, applied to the stored rewards (:126) */
+    float* theta;                         /* [N] in/out env state */
+    float* theta_dot;                     /* [N] in/out */
+    int32_t* cur_step;                    /* [N] in/out steps since reset */
+    float* states;                        /* out [H, N, 3] pre-step observation */
+    float* actions;                       /* out [H, N, 1] raw (pre-tanh) action */
+    float* logprobs;                      /* out [H, N] */
+    float* rewards;                       /* out [H, N] (already * reward_scale) */
+    uint8_t* undones;                     /* out [H, N] = !terminal */
+    uint8_t* unmasks;                     /* out [H, N] = !truncate */
+    float* values;                        /* out [H, N] V(s_t) of `critic`, or NULL */
+    float* last_state;                    /* out [N, 3] observation after the last step (agent.last_state) */
+    float* last_value;                    /* out [N] V(last_state) (reference :219-220) or NULL */
+    const float* eps;                     /* optional injected N(0,1) policy noise [H, N, 1]; NULL = Philox */
+    const float* reset_noise;             /* optional injected U[0,1) reset noise [H, N, 2]; NULL = Philox */
+    uint64_t seed;                        /* Philox key */
+    uint64_t step_offset;                 /* global step index of t = 0 (Philox counter) */
+    int64_t env_offset;                   /* global env index of local env 0 (Philox counter, multi-GPU shards) */
+} b200rl_rollout_args;
+
+B200RL_API const char* b200rl_version(void);
+B200RL_API const char* b200rl_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+B200RL_API int64_t b200rl_launch_count(void);
+
+/* Bytes of scratch the update entry points need for this pair of nets (flat gradient buffer + counters). */
+B200RL_API int64_t b200rl_workspace_bytes(const b200rl_net* actor, const b200rl_net* critic);
+/* Offset (bytes) and length (floats) of the flat fp32 gradient buffer inside the workspace: actor tensors
+ * (W0, b0, ..., action_std_log) then critic tensors.  This is the buffer a multi-GPU caller all-reduces. */
+B200RL_API int64_t b200rl_workspace_grad_offset(void);
+B200RL_API int64_t b200rl_grad_numel(const b200rl_net* actor, const b200rl_net* critic);
+
+/* net(state_norm(x)) for `rows` rows: CriticPPO.forward (AgentPPO.py:435-438; out_tanh = 0) or
+ * ActorPPO.forward (:363-366; out_tanh = 1).  x [rows, dims[0]] -> out [rows, dims[num_linear]]. */
+B200RL_API int b200rl_mlp_forward(const b200rl_net* net, const float* x, int64_t rows, float* out, int32_t out_tanh,
+                       void* stream);
+
+/* One exploration step for an arbitrary (external) vec env: ActorPPO.get_action (AgentPPO.py:368-376) +
+ * convert_action_for_env (:388-390) + optional critic value.  eps [rows, A] injected noise or NULL (Philox
+ * keyed by seed / step / env_offset + row).  Outputs: action [rows, A] (pre-tanh), logprob [rows],
+ * env_action [rows, A] = tanh(action), value [rows] (if critic and value are non-NULL). */
+B200RL_API int b200rl_policy_step(const b200rl_net* actor, const b200rl_net* critic, const float* state, int64_t rows,
+                       const float* eps, uint64_t seed, uint64_t step, int64_t env_offset, float* action,
+                       float* logprob, float* env_action, float* value, void* stream);
+
+B200RL_API int b200rl_rollout_pendulum(const b200rl_rollout_args* args, void* stream);
+
+/* AgentPPO.get_advantages (AgentPPO.py:207-232) + reward_sums (:146) + the reduction inputs of the
+ * normalisation (:149) in one reverse-scan kernel.  rewards / undones are updated IN PLACE for truncated steps
+ * exactly as the reference does (:211-214).  stat_sums (device double[4]) receives {sum(adv), sum over the
+ * [::4, ::4] lattice of adv, of adv^2, unused}; the lattice is taken on the GLOBAL env index
+ * env_offset + n so that shards agree.  A multi-GPU caller all-reduces stat_sums before b200rl_adv_stats. */
+B200RL_API int b200rl_gae(float* rewards, uint8_t* undones, const uint8_t* unmasks, const float* values,
+               const float* last_value, int32_t horizon_len, int32_t num_envs, float gamma, float lambda_gae,
+               int32_t if_use_v_trace, int64_t env_offset, float* advantages, float* reward_sums,
+               double* stat_sums, void* stream);
+/* stats_out (device float[4]) = {mean, std_unbiased(lattice), 1 / (std + 1e-5), 0} from the (all-reduced)
+ * sums.  count_all = H * N_global; count_lattice = ceil(H/4) * ceil(N_global/4). */
+B200RL_API int b200rl_adv_stats(const double* stat_sums, int64_t count_all, int64_t count_lattice, float* stats_out,
+                     void* stream);
+/* advantages = (advantages - mean) / (std + 1e-5) in place (materialises reference AgentPPO.py:149). */
+B200RL_API int b200rl_normalize_adv(float* advantages, int64_t count, const float* stats, void* stream);
+
+/* update_times minibatch updates: AgentPPO.update_net loop (AgentPPO.py:158-165) over update_objectives
+ * (:173-205) with AgentBase.optimizer_backward (AgentBase.py:239-248) per net: gather -> critic/actor
+ * forward -> losses -> backward -> per-net grad-norm clip -> Adam, all on device.
+ * ids: device int64 [update_times, batch_size] in [0, H*N) (t = id % H, n = id / H as reference :178-180) or
+ * NULL to draw them on device (Philox keyed by seed / draw_offset + update index).
+ * out_scalars (device float[3]) = mean over the updates of (obj_critic, obj_surrogate, obj_entropy)
+ * (reference :168-171).  opt->step fields are advanced on the host. */
+B200RL_API int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt,
+                      b200rl_adam* critic_opt, const b200rl_train_buffer* buffer, const b200rl_ppo_hyper* hyper,
+                      int32_t batch_size, int32_t update_times, const int64_t* ids, uint64_t seed,
+                      uint64_t draw_offset, float* out_scalars, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* Multi-GPU split of one minibatch update.  b200rl_ppo_grads leaves this rank's gradient SUM over its
+ * `local_batch` samples, already divided by `global_batch`, in the workspace's flat buffer (zeroing it first)
+ * and accumulates the three loss sums into loss_sums (device double[3], caller zeroes once per update_net);
+ * the caller all-reduces (sum) the flat buffer; b200rl_ppo_apply does clip + Adam from it on every rank. */
+B200RL_API int b200rl_ppo_grads(const b200rl_net* actor, const b200rl_net* critic, const b200rl_train_buffer* buffer,
+                     const b200rl_ppo_hyper* hyper, int32_t local_batch, int32_t global_batch,
+                     const int64_t* ids, uint64_t seed, uint64_t draw_offset, double* loss_sums,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+B200RL_API int b200rl_ppo_apply(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt,
+                     b200rl_adam* critic_opt, const b200rl_ppo_hyper* hyper, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+/* out_scalars[i] = loss_sums[i] / update_times (after the caller all-reduced loss_sums if sharded). */
+B200RL_API int b200rl_loss_means(const double* loss_sums, int32_t update_times, float* out_scalars, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */
