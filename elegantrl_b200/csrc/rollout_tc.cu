@@ -1,0 +1,351 @@
+// Fused Pendulum rollout, tcgen05 / TMEM implementation for the 3 -> 64 -> 64 -> 1 GELU actor + critic
+// (BASELINE config 2).  Same contract and outputs as rollout.cu (reference AgentPPO._explore_vec_env,
+// elegantrl/agents/AgentPPO.py:87-129, + values pass :141-143 + V(last_state) :219-220); parity vs the oracle
+// rtol 1e-4.
+//
+// Mapping.  One persistent CTA per SM owns 512 envs = 4 tiles of 128 rows for all H steps (env state in
+// registers).  1024 threads = 8 warp-groups of 128 threads: group g = (net, tile); thread <-> one env row of its
+// tile for ONE net (actor groups also step the env, critic groups also store states / values), so the two
+// nets of an env run in different warps of the same SM and every SMSP hosts 8 warps (one per group).
+//
+// Per step and group (the only dense contraction, Linear 64x64, goes to the tensor core):
+//   layer 1 (K = 3) + GELU on CUDA cores, 8 hidden units at a time -> split hi/lo (3xTF32) -> K-major A chunk
+//   [128 rows x 8] in a 2-slot shared-memory ring -> fence.proxy.async + group barrier -> one thread issues 3
+//   tcgen05.mma (Ahi*Bhi, Alo*Bhi, Ahi*Blo; M=128, N=64, K=8) accumulating in the group's 64 TMEM columns and
+//   commits to the slot's mbarrier (slot reuse) -> after the 8th chunk the accumulator is complete:
+//   tcgen05.ld 32x32b (thread = row) -> bias + GELU + dot with the output layer on CUDA cores.
+// W2 (both nets, hi/lo planes, K-major as nn.Linear stores it) stays resident in shared memory (64 KB).
+// Actor -> critic hand-off of the next observation goes through shared memory guarded by full/empty mbarriers.
+//
+// GELU: exact-erf GELU(x) = max(x,0) - 0.5|x| erfc(|x|/sqrt2), erfc(z) = exp2(-z P(z)) with a degree-5 minimax P
+// (tools/fit_gelu.py; max abs error of GELU 9.6e-7 in fp32) -- 12 issue slots instead of ~31 for erff.
+#include "rollout_params.cuh"
+#include "tc05.cuh"
+
+namespace {
+
+constexpr int kHid = 64;
+constexpr int kTileRows = 128, kTiles = 4, kRowsPerCta = kTileRows * kTiles, kThreads = 1024, kGroups = 8;
+constexpr int kChunks = kHid / 8;  // A chunks (one UMMA K-step of 8 tf32 each)
+
+// ---- dynamic shared memory map (bytes)
+constexpr int kPlaneB = kHid * kHid * 4;                   // one 64x64 fp32 plane of W2: 16 KB
+constexpr int kOffB = 0;                                   // [net][hi/lo] planes
+constexpr int kSlotBytes = 2 * kTileRows * 8 * 4;          // hi plane 4 KB + lo plane 4 KB
+constexpr int kOffRing = kOffB + 4 * kPlaneB;              // [group][slot]
+constexpr int kSmallFloats = 512;                          // per net: W1t[3][64], b1, b2, w3, b3, avg, std
+constexpr int kOffSmall = kOffRing + kGroups * 2 * kSlotBytes;
+constexpr int kOffObs = kOffSmall + 2 * kSmallFloats * 4;  // [tile][slot][3][128] fp32
+constexpr int kOffStage = kOffObs + kTiles * 2 * 3 * kTileRows * 4;   // critic warps: 16 x 96 fp32
+constexpr int kOffBars = kOffStage + 16 * 96 * 4;          // mbarriers
+constexpr int kNumBars = kGroups * 2 + kGroups + kTiles * 2 + kTiles * 2;
+constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemSlot + 16;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+// small-parameter block (float offsets)
+constexpr int kW1t = 0, kB1 = 192, kB2 = 256, kW3 = 320, kB3 = 384, kAvg = 388, kStd = 392;
+
+// GELU(x) = relu(x) - 0.5|x| * exp2(-z * P(z)), z = min(|x|/sqrt2, 4.4)   (tools/fit_gelu.py, degree 5)
+DEV float gelu_fast(float x) {
+    const float ax = fabsf(x);
+    const float z = fminf(ax * 0.70710678118654752f, 4.4f);
+    float p = -1.420747431e-04f;
+    p = fmaf(p, z, 3.664434512e-03f);
+    p = fmaf(p, z, -3.089645672e-02f);
+    p = fmaf(p, z, 1.496996325e-01f);
+    p = fmaf(p, z, 9.181654084e-01f);
+    p = fmaf(p, z, 1.627925076e+00f);
+    const float e = tc05::ex2_approx(-(p * z));
+    return fmaf(-0.5f * ax, e, fmaxf(x, 0.0f));
+}
+
+struct GroupCtx {
+    uint32_t ring_addr;     // shared address of this group's 2-slot A ring
+    uint32_t bhi_addr, blo_addr;
+    uint64_t* slot_free;    // [2]
+    uint64_t* d_ready;
+    uint32_t tmem_d;        // TMEM address (lane field = this warp's quarter, column = 64 * group)
+    int bar_id;
+    uint32_t evals;         // completed evaluations (parity source)
+    const float* small;     // this net's small-parameter block
+    uint32_t row_off;       // byte offset of this thread's row inside a chunk plane
+    bool issuer;
+};
+
+// one MLP evaluation of this group's net for this thread's row.  x = normalised observation.
+DEV float eval_net(GroupCtx& c, const float (&x)[3]) {
+    const float* sm = c.small;
+    constexpr uint32_t idesc = tc05::make_idesc_tf32(kTileRows, kHid);
+#pragma unroll 2
+    for (int ch = 0; ch < kChunks; ++ch) {
+        const int s = ch & 1;
+        const uint32_t use = c.evals * 4 + (ch >> 1);                  // how often slot s has been filled before
+        if (use > 0) tc05::mbar_wait(&c.slot_free[s], (use - 1) & 1);  // MMAs that read its previous content are done
+        float hi[8], lo[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = ch * 8 + h * 4;
+            float4 acc = *reinterpret_cast<const float4*>(sm + kB1 + j);
+            const float4 w0 = *reinterpret_cast<const float4*>(sm + kW1t + j);
+            const float4 w1 = *reinterpret_cast<const float4*>(sm + kW1t + 64 + j);
+            const float4 w2 = *reinterpret_cast<const float4*>(sm + kW1t + 128 + j);
+            acc.x = fmaf(x[0], w0.x, acc.x); acc.y = fmaf(x[0], w0.y, acc.y); acc.z = fmaf(x[0], w0.z, acc.z); acc.w = fmaf(x[0], w0.w, acc.w);
+            acc.x = fmaf(x[1], w1.x, acc.x); acc.y = fmaf(x[1], w1.y, acc.y); acc.z = fmaf(x[1], w1.z, acc.z); acc.w = fmaf(x[1], w1.w, acc.w);
+            acc.x = fmaf(x[2], w2.x, acc.x); acc.y = fmaf(x[2], w2.y, acc.y); acc.z = fmaf(x[2], w2.z, acc.z); acc.w = fmaf(x[2], w2.w, acc.w);
+            const float g[4] = {gelu_fast(acc.x), gelu_fast(acc.y), gelu_fast(acc.z), gelu_fast(acc.w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hi[h * 4 + i] = tc05::tf32_hi(g[i]);
+                lo[h * 4 + i] = g[i] - hi[h * 4 + i];
+            }
+        }
+        const uint32_t slot = c.ring_addr + s * kSlotBytes + c.row_off;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 128), "f"(hi[4]), "f"(hi[5]), "f"(hi[6]), "f"(hi[7]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096 + 128), "f"(lo[4]), "f"(lo[5]), "f"(lo[6]), "f"(lo[7]) : "memory");
+        tc05::fence_proxy_async_smem();
+        tc05::named_bar_sync(c.bar_id, kTileRows);
+        if (c.issuer) {
+            tc05::fence_after_thread_sync();
+            const uint32_t a_addr = c.ring_addr + s * kSlotBytes;
+            const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
+            const uint64_t b_hi = tc05::make_smem_desc(c.bhi_addr + ch * 256, 2048), b_lo = tc05::make_smem_desc(c.blo_addr + ch * 256, 2048);
+            const uint32_t d = c.tmem_d & 0x0000FFFFu;  // lane 0: the MMA addresses the whole 128-lane tile
+            tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
+            tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
+            tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
+            tc05::mma_commit(&c.slot_free[s]);
+            if (ch == kChunks - 1) tc05::mma_commit(c.d_ready);
+        }
+    }
+    tc05::mbar_wait(c.d_ready, c.evals & 1);
+    c.evals += 1;
+    tc05::fence_after_thread_sync();
+    float out = sm[kB3];
+#pragma unroll 1
+    for (int cc = 0; cc < kHid / 16; ++cc) {
+        float v[16];
+        tc05::tmem_ld_32x32b_x16(c.tmem_d + cc * 16, v);
+        tc05::tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b = *reinterpret_cast<const float4*>(sm + kB2 + cc * 16 + q4 * 4);
+            const float4 w = *reinterpret_cast<const float4*>(sm + kW3 + cc * 16 + q4 * 4);
+            out = fmaf(gelu_fast(v[q4 * 4 + 0] + b.x), w.x, out);
+            out = fmaf(gelu_fast(v[q4 * 4 + 1] + b.y), w.y, out);
+            out = fmaf(gelu_fast(v[q4 * 4 + 2] + b.z), w.z, out);
+            out = fmaf(gelu_fast(v[q4 * 4 + 3] + b.w), w.w, out);
+        }
+    }
+    tc05::fence_before_thread_sync();  // TMEM reads ordered before the group barrier that precedes the next MMAs
+    return out;
+}
+
+DEV void load_small(const b200rl_net& net, float* sm) {
+    for (int i = threadIdx.x; i < 3 * kHid; i += kThreads) { int k = i / kHid, j = i - k * kHid; sm[kW1t + i] = net.weight[0][j * 3 + k]; }
+    for (int i = threadIdx.x; i < kHid; i += kThreads) {
+        sm[kB1 + i] = net.bias[0][i];
+        sm[kB2 + i] = net.bias[1][i];
+        sm[kW3 + i] = net.weight[2][i];
+    }
+    if (threadIdx.x == 0) sm[kB3] = net.bias[2][0];
+    if (threadIdx.x < 3) {
+        sm[kAvg + threadIdx.x] = net.state_avg ? net.state_avg[threadIdx.x] : 0.0f;
+        sm[kStd + threadIdx.x] = net.state_std ? net.state_std[threadIdx.x] + 1e-4f : 1.0f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const __grid_constant__ RolloutParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* small = reinterpret_cast<float*>(smem + kOffSmall);
+    float* obs_sm = reinterpret_cast<float*>(smem + kOffObs);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    uint64_t* slot_free = bars;                          // [group][2]
+    uint64_t* d_ready = bars + kGroups * 2;              // [group]
+    uint64_t* obs_full = d_ready + kGroups;              // [tile][2]
+    uint64_t* obs_empty = obs_full + kTiles * 2;         // [tile][2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int net = warp >> 4, tile = (warp >> 2) & 3, quarter = warp & 3;
+    const int group = net * kTiles + tile;
+    const int row = quarter * 32 + lane;
+    const int N = P.N;
+    const int n = blockIdx.x * kRowsPerCta + tile * kTileRows + row;
+    const int n_warp0 = n - lane;
+    const bool live = n < N;
+    const bool vec_ok = (n_warp0 + 32 <= N) && ((N & 3) == 0);
+
+    // ---- one-time setup: TMEM, mbarriers, weights
+    if (warp == 0) tc05::tmem_alloc<512>(tmem_slot);
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < kGroups * 2 + kGroups; ++i) tc05::mbar_init(&bars[i], 1);
+        for (int i = 0; i < kTiles * 4; ++i) tc05::mbar_init(&obs_full[i], kTileRows);
+        tc05::mbar_fence_init();
+    }
+    for (int which = 0; which < 2; ++which) {
+        const b200rl_net& nn = which ? P.critic : P.actor;
+        float* bhi = reinterpret_cast<float*>(smem + kOffB + (which * 2 + 0) * kPlaneB);
+        float* blo = reinterpret_cast<float*>(smem + kOffB + (which * 2 + 1) * kPlaneB);
+        for (int i = threadIdx.x; i < kHid * kHid; i += kThreads) {
+            const int r = i >> 6, k = i & 63;
+            const float w = nn.weight[1][i];
+            const float h = tc05::tf32_hi(w);
+            const uint32_t off = tc05::operand_offset(r, k, kHid) >> 2;
+            bhi[off] = h;
+            blo[off] = w - h;
+        }
+        load_small(nn, small + which * kSmallFloats);
+    }
+    tc05::fence_proxy_async_smem();
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    tc05::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    GroupCtx ctx;
+    ctx.ring_addr = tc05::smem_u32(smem + kOffRing + group * 2 * kSlotBytes);
+    ctx.bhi_addr = tc05::smem_u32(smem + kOffB + (net * 2 + 0) * kPlaneB);
+    ctx.blo_addr = tc05::smem_u32(smem + kOffB + (net * 2 + 1) * kPlaneB);
+    ctx.slot_free = slot_free + group * 2;
+    ctx.d_ready = d_ready + group;
+    ctx.tmem_d = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * kHid);
+    ctx.bar_id = 1 + group;
+    ctx.evals = 0;
+    ctx.small = small + net * kSmallFloats;
+    ctx.row_off = (uint32_t)((row >> 3) * 256 + (row & 7) * 16);
+    ctx.issuer = (row == 0);
+    const float* sm = ctx.small;
+    const float avg0 = sm[kAvg], avg1 = sm[kAvg + 1], avg2 = sm[kAvg + 2];
+    const float std0 = sm[kStd], std1 = sm[kStd + 1], std2 = sm[kStd + 2];
+    const bool has_norm = net ? (P.critic.state_avg != nullptr) : (P.actor.state_avg != nullptr);
+    float* obs_tile = obs_sm + tile * (2 * 3 * kTileRows);  // [slot][3][128]
+
+    if (net == 0) {
+        // =================================================================== actor groups: policy + env
+        float theta = live ? P.theta[n] : 0.0f, theta_dot = live ? P.theta_dot[n] : 0.0f;
+        int cur_step = live ? P.cur_step[n] : 0;
+        const float sd = expf(P.actor.action_std_log[0]);
+        const float log_sd = logf(sd), var2 = __fmul_rn(2.0f, __fmul_rn(sd, sd));
+        float sin_t, cos_t;
+        sincosf(theta, &sin_t, &cos_t);
+        obs_tile[0 * kTileRows + row] = cos_t; obs_tile[1 * kTileRows + row] = sin_t; obs_tile[2 * kTileRows + row] = theta_dot;
+        tc05::mbar_arrive(&obs_full[tile * 2 + 0]);
+
+        for (int t = 0; t < P.H; ++t) {
+            const size_t rowbase = (size_t)t * N;
+            float x[3] = {cos_t, sin_t, theta_dot};
+            if (has_norm) { x[0] = (x[0] - avg0) / std0; x[1] = (x[1] - avg1) / std1; x[2] = (x[2] - avg2) / std2; }
+            const float mu = eval_net(ctx, x);
+
+            float e = 0.0f;
+            float2 reset_u = make_float2(0.0f, 0.0f);
+            if (P.eps == nullptr || P.reset_noise == nullptr) {
+                RolloutNoise nz = rollout_noise(P.seed, (uint64_t)(P.env_offset + n), P.step_offset + (uint64_t)t, 0u);
+                e = nz.normal.x;
+                reset_u = nz.uniform;
+            }
+            if (P.eps && live) e = P.eps[rowbase + n];
+            if (P.reset_noise && live) reset_u = make_float2(P.reset_noise[(rowbase + n) * 2], P.reset_noise[(rowbase + n) * 2 + 1]);
+            const float action = __fadd_rn(__fmul_rn(e, sd), mu);
+            const float diff = __fsub_rn(action, mu);
+            const float logprob = __fsub_rn(__fsub_rn(-__fdiv_rn(__fmul_rn(diff, diff), var2), log_sd), kLogSqrt2Pi);
+
+            // env.step(tanh(action))  -- same op sequence as rollout.cu / envs/pendulum.py
+            const float torque = fminf(fmaxf(__fmul_rn(tanhf(action), 2.0f), -2.0f), 2.0f);
+            const float th_n = __fsub_rn(remainder_pos(__fadd_rn(theta, kPi), kTwoPi), kPi);
+            const float cost = __fadd_rn(__fadd_rn(__fmul_rn(th_n, th_n), __fmul_rn(0.1f, __fmul_rn(theta_dot, theta_dot))),
+                                         __fmul_rn(0.001f, __fmul_rn(torque, torque)));
+            const float reward = __fmul_rn(__fmul_rn(cost, -0.5f), P.reward_scale);
+            const float accel = __fadd_rn(__fmul_rn(15.0f, sin_t), __fmul_rn(3.0f, torque));
+            float new_theta_dot = fminf(fmaxf(__fadd_rn(theta_dot, __fmul_rn(accel, 0.05f)), -8.0f), 8.0f);
+            float new_theta = __fadd_rn(theta, __fmul_rn(new_theta_dot, 0.05f));
+            cur_step += 1;
+            const bool truncate = cur_step >= P.max_step;
+            if (truncate) {
+                new_theta = __fmul_rn(__fsub_rn(__fmul_rn(reset_u.x, 2.0f), 1.0f), kPi);
+                new_theta_dot = __fsub_rn(__fmul_rn(reset_u.y, 2.0f), 1.0f);
+                cur_step = 0;
+            }
+            theta = new_theta;
+            theta_dot = new_theta_dot;
+            sincosf(theta, &sin_t, &cos_t);
+
+            // hand the next observation to the critic group of this tile (slot (t+1) & 1)
+            {
+                const int t1 = t + 1, slot = t1 & 1;
+                if (t1 >= 2) tc05::mbar_wait(&obs_empty[tile * 2 + slot], ((t1 >> 1) - 1) & 1);
+                float* o = obs_tile + slot * (3 * kTileRows);
+                o[0 * kTileRows + row] = cos_t; o[1 * kTileRows + row] = sin_t; o[2 * kTileRows + row] = theta_dot;
+                tc05::mbar_arrive(&obs_full[tile * 2 + slot]);
+            }
+            // trajectory stores owned by the actor group: action, logprob, reward, masks
+            if (live) {
+                P.actions[rowbase + n] = action;
+                P.logprobs[rowbase + n] = logprob;
+                P.rewards[rowbase + n] = reward;
+            }
+            if (vec_ok) {
+                const unsigned um_bits = __ballot_sync(0xffffffffu, !truncate);
+                if (lane < 8) {
+                    unsigned m4 = (um_bits >> (4 * lane)) & 0xFu;
+                    unsigned word = (m4 & 1u) | ((m4 & 2u) << 7) | ((m4 & 4u) << 14) | ((m4 & 8u) << 21);
+                    reinterpret_cast<unsigned*>(P.unmasks + rowbase + n_warp0)[lane] = word;
+                    reinterpret_cast<unsigned*>(P.undones + rowbase + n_warp0)[lane] = 0x01010101u;
+                }
+            } else if (live) {
+                P.unmasks[rowbase + n] = truncate ? 0 : 1;
+                P.undones[rowbase + n] = 1;
+            }
+        }
+        if (live) { P.theta[n] = theta; P.theta_dot[n] = theta_dot; P.cur_step[n] = cur_step; }
+    } else {
+        // ============================================== critic groups: V(s_t), state stores, V(last_state)
+        float* my_stage = reinterpret_cast<float*>(smem + kOffStage) + (warp - 16) * 96;
+        for (int t = 0; t <= P.H; ++t) {
+            const int slot = t & 1;
+            tc05::mbar_wait(&obs_full[tile * 2 + slot], (t >> 1) & 1);
+            const float* o = obs_tile + slot * (3 * kTileRows);
+            const float obs0 = o[0 * kTileRows + row], obs1 = o[1 * kTileRows + row], obs2 = o[2 * kTileRows + row];
+            tc05::mbar_arrive(&obs_empty[tile * 2 + slot]);
+            float x[3] = {obs0, obs1, obs2};
+            if (has_norm) { x[0] = (x[0] - avg0) / std0; x[1] = (x[1] - avg1) / std1; x[2] = (x[2] - avg2) / std2; }
+            const float val = eval_net(ctx, x);
+            const bool last = (t == P.H);
+            float* dst_states = last ? P.last_state : P.states + (size_t)t * N * 3;
+            if (vec_ok) {
+                my_stage[lane * 3 + 0] = obs0; my_stage[lane * 3 + 1] = obs1; my_stage[lane * 3 + 2] = obs2;
+                __syncwarp();
+                if (lane < 24) reinterpret_cast<float4*>(dst_states + (size_t)n_warp0 * 3)[lane] = *reinterpret_cast<const float4*>(my_stage + 4 * lane);
+                __syncwarp();
+            } else if (live) {
+                dst_states[(size_t)n * 3 + 0] = obs0; dst_states[(size_t)n * 3 + 1] = obs1; dst_states[(size_t)n * 3 + 2] = obs2;
+            }
+            if (live) {
+                if (!last) { if (P.values) P.values[(size_t)t * N + n] = val; }
+                else if (P.last_value) P.last_value[n] = val;
+            }
+        }
+    }
+
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+int b200rl_launch_rollout_tc(const RolloutParams& P, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        B200RL_CHECK_CUDA(cudaFuncSetAttribute(rollout_pendulum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    const int grid = (P.N + kRowsPerCta - 1) / kRowsPerCta;
+    rollout_pendulum_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(P);
+    B200RL_COUNT_LAUNCH(1);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -285,8 +285,15 @@ def test_update_device_sampled_indices():
 
 
 # ---------------------------------------------------------------------------------------- rollout
+@pytest.fixture(params=["tc", "ffma"])
+def rollout_impl(request, monkeypatch):
+    """Both fused-rollout implementations (tcgen05 / TMEM and FP32-pipe) must agree with the reference."""
+    monkeypatch.setenv("B200RL_ROLLOUT", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("case", gu.ROLLOUT_CASES)
-def test_fused_rollout_against_reference(case):
+def test_fused_rollout_against_reference(case, rollout_impl):
     from elegantrl_b200.envs import PendulumVecEnv
     g = gu.load(case)
     agent = G.agent_from_golden(g)
@@ -315,8 +322,8 @@ def test_fused_rollout_against_reference(case):
     G.assert_close(np.array(result), g["update_net.result"], RTOL, 1e-6)
 
 
-@pytest.mark.parametrize("n", [1, 31, 33, 70, 130])
-def test_fused_rollout_ragged_env_counts(n):
+@pytest.mark.parametrize("n", [1, 31, 33, 70, 130, 515, 1100])
+def test_fused_rollout_ragged_env_counts(n, rollout_impl):
     """Partial warps / unaligned rows take the scalar store path; must equal the oracle all the same."""
     from elegantrl_b200.envs import PendulumVecEnv
     g = gu.load("rollout_pendulum_n8_h16")
@@ -341,7 +348,7 @@ def test_fused_rollout_ragged_env_counts(n):
     G.assert_close(agent._value_cache[1], want["values"], RTOL, 1e-5)
 
 
-def test_fused_rollout_matches_torch_env_stepwise():
+def test_fused_rollout_matches_torch_env_stepwise(rollout_impl):
     """The fused kernel and the per-step path (engine policy step + torch env.step) walk the same trajectory when
     fed the same noise -- the vec-env contract the reference's loop relies on (AgentPPO.py:112-123)."""
     from elegantrl_b200.envs import PendulumVecEnv
