@@ -39,7 +39,7 @@ int64_t b200rl_launch_count(void) { return (int64_t)g_b200rl_launches; }
 
 int64_t b200rl_grad_numel(const b200rl_net* actor, const b200rl_net* critic) {
     if (!actor || !critic) return -1;
-    return b200rl_net_numel(actor) + b200rl_net_numel(critic);
+    return ((b200rl_net_numel(actor) + 3) & ~(int64_t)3) + b200rl_net_numel(critic);  // critic segment 16-byte aligned
 }
 int64_t b200rl_workspace_grad_offset(void) { return B200RL_WS_HEADER_BYTES; }
 int64_t b200rl_workspace_bytes(const b200rl_net* actor, const b200rl_net* critic) {

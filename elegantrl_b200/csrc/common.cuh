@@ -43,12 +43,12 @@ int b200rl_validate_net(const b200rl_net* net, const char* name, bool is_actor);
 extern long long g_b200rl_launches;  // kernels launched by this library in this process (b200rl_launch_count)
 #define B200RL_COUNT_LAUNCH(n) (g_b200rl_launches += (n))
 
-// workspace layout (bytes): [0, 256) header {double loss_sums[4]; unsigned ticket; ...}; [256, ...) flat grads
+// workspace layout (bytes): [0, 256) header {double loss_sums[4]; unsigned ticket[2]; ...}; [256, ...) flat grads
 #define B200RL_WS_HEADER_BYTES 256
 struct WorkspaceHeader {
     double loss_sums[4];
-    unsigned int ticket;
-    unsigned int pad[3];
+    unsigned int ticket[2];  // per net: CTAs of the running minibatch that finished their gradient phase
+    unsigned int pad[2];
 };
 
 // ------------------------------------------------------------------------------------------- math

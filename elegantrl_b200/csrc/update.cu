@@ -136,6 +136,14 @@ DEV float block_sum(float v, float* red /*[32]*/) {
     return t;
 }
 
+// torch.optim.Adam single-tensor update, op order of torch (_single_tensor_adam), no FMA contraction
+DEV void adam_one(float& p, float& m, float& v, float g, float b1, float b2, float eps, const AdamScalars& as) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - b1));                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(1.0f - b2, g), g));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), as.bc2_sqrt), eps);
+    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-as.step_size, m), denom));         // addcdiv_(exp_avg, denom, -step_size)
+}
+
 // clip_grad_norm_ + Adam.step for one net, executed by one whole CTA.
 DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
                    float clip_grad_norm, float* red) {
@@ -161,14 +169,26 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
         } else {
             p = net.bias[l]; m = opt.exp_avg_b[l]; v = opt.exp_avg_sq_b[l]; count = net.dims[l + 1];
         }
-        for (int i = threadIdx.x; i < count; i += kUpdThreads) {
-            float gi = __ldcg(g + off + i) * coef;
-            float mi = m[i], vi = v[i];
-            mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), 1.0f - b1));                 // exp_avg.lerp_(grad, 1 - beta1)
-            vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(__fmul_rn(1.0f - b2, gi), gi));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
-            float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), as.bc2_sqrt), eps);
-            p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(-as.step_size, mi), denom));      // addcdiv_(exp_avg, denom, -step_size)
-            m[i] = mi; v[i] = vi;
+        const bool vec = ((count & 3) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(g + off) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) |
+                            reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+        if (vec) {  // 128-bit path: four independent parameter lanes per thread and iteration
+            const float4* g4 = reinterpret_cast<const float4*>(g + off);
+            float4 *p4 = reinterpret_cast<float4*>(p), *m4 = reinterpret_cast<float4*>(m), *v4 = reinterpret_cast<float4*>(v);
+            for (int i = threadIdx.x; i < (count >> 2); i += kUpdThreads) {
+                float4 gg = __ldcg(g4 + i), pp = p4[i], mm = m4[i], vv = v4[i];
+                adam_one(pp.x, mm.x, vv.x, gg.x * coef, b1, b2, eps, as);
+                adam_one(pp.y, mm.y, vv.y, gg.y * coef, b1, b2, eps, as);
+                adam_one(pp.z, mm.z, vv.z, gg.z * coef, b1, b2, eps, as);
+                adam_one(pp.w, mm.w, vv.w, gg.w * coef, b1, b2, eps, as);
+                p4[i] = pp; m4[i] = mm; v4[i] = vv;
+            }
+        } else {
+            for (int i = threadIdx.x; i < count; i += kUpdThreads) {
+                float pi = p[i], mi = m[i], vi = v[i];
+                adam_one(pi, mi, vi, __ldcg(g + off + i) * coef, b1, b2, eps, as);
+                p[i] = pi; m[i] = mi; v[i] = vi;
+            }
         }
         off += count;
     }
@@ -214,9 +234,10 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     const float inv_bsz = 1.0f / (float)A.global_batch;
     float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;  // valid in threads < UTB
 
-    // ---- critic (net 1) then actor (net 0): the nets are disjoint, order is immaterial (reference :189-204)
-    for (int pass = 0; pass < 2; ++pass) {
-        const int ni = 1 - pass;
+    // ---- blockIdx.y selects the net: the critic and actor updates are disjoint (reference :189-204 steps the critic
+    //      first, but neither net reads the other's parameters), so they run as concurrent CTAs
+    const int ni = blockIdx.y;
+    {
         const b200rl_net& net = A.net[ni];
         const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
         // smem map: X[0..L-1] (inputs of each Linear), G[1..L-1] (act' at each hidden layer), dzA, dzB
@@ -313,24 +334,23 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     }
     if (!A.fused_apply) return;
 
-    // ---- last block done: clip + Adam for both nets, then re-zero the gradient buffer
+    // ---- last block done (per net): clip + Adam for this net, then re-zero its slice of the gradient buffer
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&A.hdr->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&A.hdr->ticket[ni], 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int ni = 0; ni < 2; ++ni)
-        apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+    apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
     __syncthreads();
-    for (int i = threadIdx.x; i < A.grad_numel[0] + A.grad_numel[1]; i += kUpdThreads) A.grads[i] = 0.0f;
-    if (threadIdx.x == 0) A.hdr->ticket = 0u;
+    for (int i = threadIdx.x; i < A.grad_numel[ni]; i += kUpdThreads) A.grads[A.grad_off[ni] + i] = 0.0f;
+    if (threadIdx.x == 0) A.hdr->ticket[ni] = 0u;
 }
 
 __global__ void __launch_bounds__(kUpdThreads) ppo_apply_kernel(const __grid_constant__ UpdateArgs A) {
     __shared__ float red[32];
-    for (int ni = 0; ni < 2; ++ni)
-        apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+    const int ni = blockIdx.x;  // one CTA per net
+    apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
 }
 
 __global__ void loss_means_kernel(const double* loss_sums, double inv_updates, float* out) {
@@ -368,7 +388,7 @@ int fill_args(UpdateArgs& A, const b200rl_net* actor, const b200rl_net* critic, 
     A.grad_numel[0] = (int)b200rl_net_numel(actor);
     A.grad_numel[1] = (int)b200rl_net_numel(critic);
     A.grad_off[0] = 0;
-    A.grad_off[1] = A.grad_numel[0];
+    A.grad_off[1] = (A.grad_numel[0] + 3) & ~3;  // 16-byte aligned start of the critic segment
     // dynamic smem: max over nets of (sum of Linear input dims + sum of hidden dims) + 2 * maxdim, + scalars
     int maxdim = 0, rows = 0;
     for (int ni = 0; ni < 2; ++ni) {
@@ -417,7 +437,7 @@ int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* critic, b200rl_
     A.seed = seed;
     B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200RL_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)b200rl_workspace_bytes(actor, critic), stream));
-    const unsigned grid = (unsigned)((batch_size + UTB - 1) / UTB);
+    const dim3 grid((unsigned)((batch_size + UTB - 1) / UTB), 2);
     for (int u = 0; u < update_times; ++u) {
         A.ids = ids ? ids + (size_t)u * batch_size : nullptr;
         A.draw = draw_offset + (uint64_t)u;
@@ -454,8 +474,8 @@ int b200rl_ppo_grads(const b200rl_net* actor, const b200rl_net* critic, const b2
     A.seed = seed;
     A.draw = draw_offset;
     B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200RL_CHECK_CUDA(cudaMemsetAsync(A.grads, 0, (size_t)(A.grad_numel[0] + A.grad_numel[1]) * sizeof(float), stream));
-    ppo_grads_kernel<<<(unsigned)((local_batch + UTB - 1) / UTB), kUpdThreads, smem, stream>>>(A);
+    B200RL_CHECK_CUDA(cudaMemsetAsync(A.grads, 0, (size_t)(A.grad_off[1] + A.grad_numel[1]) * sizeof(float), stream));
+    ppo_grads_kernel<<<dim3((unsigned)((local_batch + UTB - 1) / UTB), 2), kUpdThreads, smem, stream>>>(A);
     B200RL_COUNT_LAUNCH(1);
     B200RL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -469,7 +489,7 @@ int b200rl_ppo_apply(const b200rl_net* actor, const b200rl_net* critic, b200rl_a
     if (int rc = fill_args(A, actor, critic, actor_opt, critic_opt, nullptr, hyper, workspace, workspace_bytes, &smem)) return rc;
     A.adam[0] = adam_scalars(actor_opt, actor_opt->step + 1);
     A.adam[1] = adam_scalars(critic_opt, critic_opt->step + 1);
-    ppo_apply_kernel<<<1, kUpdThreads, 0, (cudaStream_t)stream_>>>(A);
+    ppo_apply_kernel<<<2, kUpdThreads, 0, (cudaStream_t)stream_>>>(A);
     B200RL_COUNT_LAUNCH(1);
     B200RL_CHECK_CUDA(cudaGetLastError());
     actor_opt->step += 1;

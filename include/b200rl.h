@@ -124,7 +124,8 @@ B200RL_API int64_t b200rl_launch_count(void);
 /* Bytes of scratch the update entry points need for this pair of nets (flat gradient buffer + counters). */
 B200RL_API int64_t b200rl_workspace_bytes(const b200rl_net* actor, const b200rl_net* critic);
 /* Offset (bytes) and length (floats) of the flat fp32 gradient buffer inside the workspace: actor tensors
- * (W0, b0, ..., action_std_log) then critic tensors.  This is the buffer a multi-GPU caller all-reduces. */
+ * (W0, b0, ..., action_std_log), zero padding up to a multiple of 4 floats, then critic tensors.  This is the
+ * buffer a multi-GPU caller all-reduces (b200rl_grad_numel includes the padding). */
 B200RL_API int64_t b200rl_workspace_grad_offset(void);
 B200RL_API int64_t b200rl_grad_numel(const b200rl_net* actor, const b200rl_net* critic);
 
