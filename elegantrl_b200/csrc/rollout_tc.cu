@@ -3,19 +3,23 @@
 // elegantrl/agents/AgentPPO.py:87-129, + values pass :141-143 + V(last_state) :219-220); parity vs the oracle
 // rtol 1e-4.
 //
-// Mapping.  One persistent CTA per SM owns 512 envs = 4 tiles of 128 rows for all H steps (env state in
-// registers).  1024 threads = 8 warp-groups of 128 threads: group g = (net, tile); thread <-> one env row of its
-// tile for ONE net (actor groups also step the env, critic groups also store states / values), so the two
-// nets of an env run in different warps of the same SM and every SMSP hosts 8 warps (one per group).
+// Mapping.  One persistent CTA per SM owns 448 envs = 3.5 tiles of 128 rows for all H steps (65 536 envs ->
+// 147 CTAs on 148 SMs; env state lives in registers).  896 threads = 28 warps = 7 per SM sub-partition.  A warp
+// serves ONE net for 32 env rows: 8 warp-groups g = (net, tile); the half tile has 2 warps per net, the
+// actor's on TMEM lane quarters 0-1 and the critic's on quarters 2-3 (a warp may only touch TMEM lanes
+// 32 * (warp_id % 4) .. +31, and both nets keep separate A operands / accumulators, so each net can place the 64
+// live rows of the half tile where its warp ids allow).  Actor warps also step the env and own the action /
+// logprob / reward / mask stores, critic warps own the state / value stores; the next observation goes from
+// actor to critic through shared memory guarded by full / empty mbarriers.
 //
 // Per step and group (the only dense contraction, Linear 64x64, goes to the tensor core):
 //   layer 1 (K = 3) + GELU on CUDA cores, 8 hidden units at a time -> split hi/lo (3xTF32) -> K-major A chunk
-//   [128 rows x 8] in a 2-slot shared-memory ring -> fence.proxy.async + group barrier -> one thread issues 3
-//   tcgen05.mma (Ahi*Bhi, Alo*Bhi, Ahi*Blo; M=128, N=64, K=8) accumulating in the group's 64 TMEM columns and
-//   commits to the slot's mbarrier (slot reuse) -> after the 8th chunk the accumulator is complete:
-//   tcgen05.ld 32x32b (thread = row) -> bias + GELU + dot with the output layer on CUDA cores.
-// W2 (both nets, hi/lo planes, K-major as nn.Linear stores it) stays resident in shared memory (64 KB).
-// Actor -> critic hand-off of the next observation goes through shared memory guarded by full/empty mbarriers.
+//   [128 rows x 8] in a 2-slot shared-memory ring -> fence.proxy.async + warp-aggregated acq_rel counter; the
+//   LAST warp of the group to arrive issues 3 tcgen05.mma (Ahi*Bhi, Alo*Bhi, Ahi*Blo; M=128, N=64, K=8) into the
+//   group's 64 TMEM columns and commits to the slot's mbarrier (slot reuse) -- no warp ever blocks on its peers;
+//   after the 8th chunk the accumulator is complete: tcgen05.ld 32x32b (thread = row) -> bias + GELU + dot with
+//   the output layer on CUDA cores.
+// W2 (both nets, hi/lo planes, K-major exactly as nn.Linear stores it) stays resident in shared memory (64 KB).
 //
 // GELU: exact-erf GELU(x) = max(x,0) - 0.5|x| erfc(|x|/sqrt2), erfc(z) = exp2(-z P(z)) with a degree-5 minimax P
 // (tools/fit_gelu.py; max abs error of GELU 9.6e-7 in fp32) -- 12 issue slots instead of ~31 for erff.
@@ -25,7 +29,7 @@
 namespace {
 
 constexpr int kHid = 64;
-constexpr int kTileRows = 128, kTiles = 4, kRowsPerCta = kTileRows * kTiles, kThreads = 1024, kGroups = 8;
+constexpr int kTileRows = 128, kTiles = 4, kRowsPerCta = 448, kWarps = 28, kThreads = kWarps * 32, kGroups = 8;
 constexpr int kChunks = kHid / 8;  // A chunks (one UMMA K-step of 8 tf32 each)
 
 // ---- dynamic shared memory map (bytes)
@@ -36,10 +40,11 @@ constexpr int kOffRing = kOffB + 4 * kPlaneB;              // [group][slot]
 constexpr int kSmallFloats = 512;                          // per net: W1t[3][64], b1, b2, w3, b3, avg, std
 constexpr int kOffSmall = kOffRing + kGroups * 2 * kSlotBytes;
 constexpr int kOffObs = kOffSmall + 2 * kSmallFloats * 4;  // [tile][slot][3][128] fp32
-constexpr int kOffStage = kOffObs + kTiles * 2 * 3 * kTileRows * 4;   // critic warps: 16 x 96 fp32
-constexpr int kOffBars = kOffStage + 16 * 96 * 4;          // mbarriers
+constexpr int kOffStage = kOffObs + kTiles * 2 * 3 * kTileRows * 4;   // critic warps: 14 x 96 fp32
+constexpr int kOffBars = kOffStage + 14 * 96 * 4;          // mbarriers
 constexpr int kNumBars = kGroups * 2 + kGroups + kTiles * 2 + kTiles * 2;
-constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+constexpr int kOffFill = kOffBars + kNumBars * 8;          // [group][2] uint32 arrival counters
+constexpr int kOffTmemSlot = kOffFill + kGroups * 2 * 4;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -60,28 +65,33 @@ DEV float gelu_fast(float x) {
     return fmaf(-0.5f * ax, e, fmaxf(x, 0.0f));
 }
 
+DEV uint32_t atom_add_acq_rel_smem(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(tc05::smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
 struct GroupCtx {
     uint32_t ring_addr;     // shared address of this group's 2-slot A ring
     uint32_t bhi_addr, blo_addr;
     uint64_t* slot_free;    // [2]
     uint64_t* d_ready;
+    uint32_t* fill;         // [2] arrival counters of the two ring slots (monotonic)
     uint32_t tmem_d;        // TMEM address (lane field = this warp's quarter, column = 64 * group)
-    int bar_id;
+    uint32_t group_warps;   // 4, or 2 for the half tile
     uint32_t evals;         // completed evaluations (parity source)
     const float* small;     // this net's small-parameter block
     uint32_t row_off;       // byte offset of this thread's row inside a chunk plane
-    bool issuer;
 };
 
 // one MLP evaluation of this group's net for this thread's row.  x = normalised observation.
-DEV float eval_net(GroupCtx& c, const float (&x)[3]) {
+DEV float eval_net(GroupCtx& c, const float (&x)[3], int lane) {
     const float* sm = c.small;
     constexpr uint32_t idesc = tc05::make_idesc_tf32(kTileRows, kHid);
 #pragma unroll 2
     for (int ch = 0; ch < kChunks; ++ch) {
         const int s = ch & 1;
-        const uint32_t use = c.evals * 4 + (ch >> 1);                  // how often slot s has been filled before
-        if (use > 0) tc05::mbar_wait(&c.slot_free[s], (use - 1) & 1);  // MMAs that read its previous content are done
+        const uint32_t use = c.evals * 4 + (ch >> 1);  // how often slot s has been filled before
         float hi[8], lo[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -100,25 +110,32 @@ DEV float eval_net(GroupCtx& c, const float (&x)[3]) {
                 lo[h * 4 + i] = g[i] - hi[h * 4 + i];
             }
         }
+        // the MMAs that read the previous content of slot s must be done before it is overwritten
+        if (use > 0) tc05::mbar_wait(&c.slot_free[s], (use - 1) & 1);
         const uint32_t slot = c.ring_addr + s * kSlotBytes + c.row_off;
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 128), "f"(hi[4]), "f"(hi[5]), "f"(hi[6]), "f"(hi[7]) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096 + 128), "f"(lo[4]), "f"(lo[5]), "f"(lo[6]), "f"(lo[7]) : "memory");
         tc05::fence_proxy_async_smem();
-        tc05::named_bar_sync(c.bar_id, kTileRows);
-        if (c.issuer) {
-            tc05::fence_after_thread_sync();
-            const uint32_t a_addr = c.ring_addr + s * kSlotBytes;
-            const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
-            const uint64_t b_hi = tc05::make_smem_desc(c.bhi_addr + ch * 256, 2048), b_lo = tc05::make_smem_desc(c.blo_addr + ch * 256, 2048);
-            const uint32_t d = c.tmem_d & 0x0000FFFFu;  // lane 0: the MMA addresses the whole 128-lane tile
-            tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
-            tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
-            tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
-            tc05::mma_commit(&c.slot_free[s]);
-            if (ch == kChunks - 1) tc05::mma_commit(c.d_ready);
+        __syncwarp();
+        // warp-aggregated arrival; the last warp of the group issues this chunk's MMAs
+        if (lane == 0) {
+            const uint32_t old = atom_add_acq_rel_smem(&c.fill[s], 1u);
+            if (old == c.group_warps * (use + 1) - 1) {
+                tc05::fence_after_thread_sync();
+                const uint32_t a_addr = c.ring_addr + s * kSlotBytes;
+                const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
+                const uint64_t b_hi = tc05::make_smem_desc(c.bhi_addr + ch * 256, 2048), b_lo = tc05::make_smem_desc(c.blo_addr + ch * 256, 2048);
+                const uint32_t d = c.tmem_d & 0x0000FFFFu;  // lane 0: the MMA addresses the whole 128-lane tile
+                tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
+                tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
+                tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
+                tc05::mma_commit(&c.slot_free[s]);
+                if (ch == kChunks - 1) tc05::mma_commit(c.d_ready);
+            }
         }
+        __syncwarp();
     }
     tc05::mbar_wait(c.d_ready, c.evals & 1);
     c.evals += 1;
@@ -139,7 +156,8 @@ DEV float eval_net(GroupCtx& c, const float (&x)[3]) {
             out = fmaf(gelu_fast(v[q4 * 4 + 3] + b.w), w.w, out);
         }
     }
-    tc05::fence_before_thread_sync();  // TMEM reads ordered before the group barrier that precedes the next MMAs
+    // TMEM reads of this evaluation are ordered before the (release) arrival that precedes the next evaluation's MMAs
+    tc05::fence_before_thread_sync();
     return out;
 }
 
@@ -166,14 +184,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
     uint64_t* d_ready = bars + kGroups * 2;              // [group]
     uint64_t* obs_full = d_ready + kGroups;              // [tile][2]
     uint64_t* obs_empty = obs_full + kTiles * 2;         // [tile][2]
+    uint32_t* fill = reinterpret_cast<uint32_t*>(smem + kOffFill);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
 
+    // ---- warp roles (see file header): warp_id % 4 is always the TMEM lane quarter the warp works on
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int net = warp >> 4, tile = (warp >> 2) & 3, quarter = warp & 3;
+    int net, tile, critic_warp;
+    if (warp < 24) { net = warp / 12; tile = (warp % 12) >> 2; critic_warp = warp - 12; }
+    else { net = (warp - 24) >> 1; tile = 3; critic_warp = 12 + (warp - 26); }
+    const int quarter = warp & 3;
     const int group = net * kTiles + tile;
-    const int row = quarter * 32 + lane;
+    const int row = quarter * 32 + lane;                              // A / accumulator row inside the tile
+    const int env_in_tile = (tile == 3 && net == 1) ? row - 64 : row; // half tile: critic rows 64..127 <-> envs 0..63
+    const int tile_envs = tile == 3 ? 64 : 128;
     const int N = P.N;
-    const int n = blockIdx.x * kRowsPerCta + tile * kTileRows + row;
+    const int n = blockIdx.x * kRowsPerCta + tile * kTileRows + env_in_tile;
     const int n_warp0 = n - lane;
     const bool live = n < N;
     const bool vec_ok = (n_warp0 + 32 <= N) && ((N & 3) == 0);
@@ -182,9 +207,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
     if (warp == 0) tc05::tmem_alloc<512>(tmem_slot);
     if (threadIdx.x == 32) {
         for (int i = 0; i < kGroups * 2 + kGroups; ++i) tc05::mbar_init(&bars[i], 1);
-        for (int i = 0; i < kTiles * 4; ++i) tc05::mbar_init(&obs_full[i], kTileRows);
+        for (int t = 0; t < kTiles; ++t)
+            for (int sl = 0; sl < 2; ++sl) {
+                tc05::mbar_init(&obs_full[t * 2 + sl], t == 3 ? 64 : 128);
+                tc05::mbar_init(&obs_empty[t * 2 + sl], t == 3 ? 64 : 128);
+            }
         tc05::mbar_fence_init();
     }
+    if (threadIdx.x < kGroups * 2) fill[threadIdx.x] = 0u;
     for (int which = 0; which < 2; ++which) {
         const b200rl_net& nn = which ? P.critic : P.actor;
         float* bhi = reinterpret_cast<float*>(smem + kOffB + (which * 2 + 0) * kPlaneB);
@@ -199,6 +229,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
         }
         load_small(nn, small + which * kSmallFloats);
     }
+    // rows of the half tile's A operands that no thread ever writes: keep them finite (they feed unused TMEM lanes)
+    for (int i = threadIdx.x; i < 2 * 2 * kSlotBytes / 4; i += kThreads) {
+        const int g = (i < 2 * kSlotBytes / 4) ? 3 : 7;
+        reinterpret_cast<float*>(smem + kOffRing + g * 2 * kSlotBytes)[i % (2 * kSlotBytes / 4)] = 0.0f;
+    }
     tc05::fence_proxy_async_smem();
     tc05::fence_before_thread_sync();
     __syncthreads();
@@ -211,34 +246,35 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
     ctx.blo_addr = tc05::smem_u32(smem + kOffB + (net * 2 + 1) * kPlaneB);
     ctx.slot_free = slot_free + group * 2;
     ctx.d_ready = d_ready + group;
+    ctx.fill = fill + group * 2;
     ctx.tmem_d = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * kHid);
-    ctx.bar_id = 1 + group;
+    ctx.group_warps = tile == 3 ? 2u : 4u;
     ctx.evals = 0;
     ctx.small = small + net * kSmallFloats;
     ctx.row_off = (uint32_t)((row >> 3) * 256 + (row & 7) * 16);
-    ctx.issuer = (row == 0);
     const float* sm = ctx.small;
     const float avg0 = sm[kAvg], avg1 = sm[kAvg + 1], avg2 = sm[kAvg + 2];
     const float std0 = sm[kStd], std1 = sm[kStd + 1], std2 = sm[kStd + 2];
     const bool has_norm = net ? (P.critic.state_avg != nullptr) : (P.actor.state_avg != nullptr);
-    float* obs_tile = obs_sm + tile * (2 * 3 * kTileRows);  // [slot][3][128]
+    float* obs_tile = obs_sm + tile * (2 * 3 * kTileRows);  // [slot][3][128], indexed by env_in_tile
+    (void)tile_envs;
 
     if (net == 0) {
-        // =================================================================== actor groups: policy + env
+        // =================================================================== actor warps: policy + env
         float theta = live ? P.theta[n] : 0.0f, theta_dot = live ? P.theta_dot[n] : 0.0f;
         int cur_step = live ? P.cur_step[n] : 0;
         const float sd = expf(P.actor.action_std_log[0]);
         const float log_sd = logf(sd), var2 = __fmul_rn(2.0f, __fmul_rn(sd, sd));
         float sin_t, cos_t;
         sincosf(theta, &sin_t, &cos_t);
-        obs_tile[0 * kTileRows + row] = cos_t; obs_tile[1 * kTileRows + row] = sin_t; obs_tile[2 * kTileRows + row] = theta_dot;
+        obs_tile[0 * kTileRows + env_in_tile] = cos_t; obs_tile[1 * kTileRows + env_in_tile] = sin_t; obs_tile[2 * kTileRows + env_in_tile] = theta_dot;
         tc05::mbar_arrive(&obs_full[tile * 2 + 0]);
 
         for (int t = 0; t < P.H; ++t) {
             const size_t rowbase = (size_t)t * N;
             float x[3] = {cos_t, sin_t, theta_dot};
             if (has_norm) { x[0] = (x[0] - avg0) / std0; x[1] = (x[1] - avg1) / std1; x[2] = (x[2] - avg2) / std2; }
-            const float mu = eval_net(ctx, x);
+            const float mu = eval_net(ctx, x, lane);
 
             float e = 0.0f;
             float2 reset_u = make_float2(0.0f, 0.0f);
@@ -273,15 +309,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
             theta_dot = new_theta_dot;
             sincosf(theta, &sin_t, &cos_t);
 
-            // hand the next observation to the critic group of this tile (slot (t+1) & 1)
+            // hand the next observation to the critic warps of this tile (slot (t+1) & 1)
             {
                 const int t1 = t + 1, slot = t1 & 1;
                 if (t1 >= 2) tc05::mbar_wait(&obs_empty[tile * 2 + slot], ((t1 >> 1) - 1) & 1);
                 float* o = obs_tile + slot * (3 * kTileRows);
-                o[0 * kTileRows + row] = cos_t; o[1 * kTileRows + row] = sin_t; o[2 * kTileRows + row] = theta_dot;
+                o[0 * kTileRows + env_in_tile] = cos_t; o[1 * kTileRows + env_in_tile] = sin_t; o[2 * kTileRows + env_in_tile] = theta_dot;
                 tc05::mbar_arrive(&obs_full[tile * 2 + slot]);
             }
-            // trajectory stores owned by the actor group: action, logprob, reward, masks
+            // trajectory stores owned by the actor warps: action, logprob, reward, masks
             if (live) {
                 P.actions[rowbase + n] = action;
                 P.logprobs[rowbase + n] = logprob;
@@ -302,17 +338,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
         }
         if (live) { P.theta[n] = theta; P.theta_dot[n] = theta_dot; P.cur_step[n] = cur_step; }
     } else {
-        // ============================================== critic groups: V(s_t), state stores, V(last_state)
-        float* my_stage = reinterpret_cast<float*>(smem + kOffStage) + (warp - 16) * 96;
+        // ============================================== critic warps: V(s_t), state stores, V(last_state)
+        float* my_stage = reinterpret_cast<float*>(smem + kOffStage) + critic_warp * 96;
         for (int t = 0; t <= P.H; ++t) {
             const int slot = t & 1;
             tc05::mbar_wait(&obs_full[tile * 2 + slot], (t >> 1) & 1);
             const float* o = obs_tile + slot * (3 * kTileRows);
-            const float obs0 = o[0 * kTileRows + row], obs1 = o[1 * kTileRows + row], obs2 = o[2 * kTileRows + row];
+            const float obs0 = o[0 * kTileRows + env_in_tile], obs1 = o[1 * kTileRows + env_in_tile], obs2 = o[2 * kTileRows + env_in_tile];
             tc05::mbar_arrive(&obs_empty[tile * 2 + slot]);
             float x[3] = {obs0, obs1, obs2};
             if (has_norm) { x[0] = (x[0] - avg0) / std0; x[1] = (x[1] - avg1) / std1; x[2] = (x[2] - avg2) / std2; }
-            const float val = eval_net(ctx, x);
+            const float val = eval_net(ctx, x, lane);
             const bool last = (t == P.H);
             float* dst_states = last ? P.last_state : P.states + (size_t)t * N * 3;
             if (vec_ok) {
