@@ -52,3 +52,29 @@ if __name__ == "__main__":
         err = np.abs(g.astype(np.float64) - exact)
         print(f"deg {deg}: max abs erf-fit err {e_erf:.2e}; GELU f32 max abs err {err.max():.2e} at x={x[err.argmax()]:.3f}")
         print("   coef (q*log2e, increasing powers of z):", ", ".join(f"{c:.9e}f" for c in coef2))
+
+
+def packed_form(deg=5):
+    """Coefficients of the form used by gelu_fast2 in csrc/rollout_tc.cu:
+    zn = -min(|x|, L); t = zn * Pt(zn) - 1; GELU = max(x, 0) + zn * exp2(t)   (0.5 * erfc folded into the -1)."""
+    coef, _ = fit(deg)
+    a = coef * LOG2E
+    s = 0.7071067811865476
+    pt = [a[k] * s ** (k + 1) * (-1) ** k for k in range(deg + 1)]
+    L = ZMAX / s
+    x = np.linspace(-9, 9, 2_000_001).astype(np.float32)
+    exact = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+    zn = np.maximum(-np.abs(x), np.float32(-L)).astype(np.float32)
+    p = np.float32(pt[-1])
+    for c in pt[-2::-1]:
+        p = (p * zn + np.float32(c)).astype(np.float32)
+    t = (p * zn + np.float32(-1.0)).astype(np.float32)
+    e = np.exp2(t.astype(np.float64)).astype(np.float32)
+    g = (zn * e + np.maximum(x, np.float32(0))).astype(np.float32)
+    err = np.abs(g.astype(np.float64) - exact)
+    print(f"packed form deg {deg}: L = {L:.7f}; GELU f32 max abs err {err.max():.2e} at x={x[err.argmax()]:.3f}")
+    print("   Pt (increasing powers of zn):", ", ".join(f"{c:.9e}f" for c in pt))
+
+
+if __name__ == "__main__":
+    packed_form(5)
