@@ -1,0 +1,3 @@
+from .run import train_agent
+
+__all__ = ["train_agent"]

@@ -418,3 +418,50 @@ def net_astype(net, dtype):
         if net.get(k) is not None:
             out[k] = net[k].astype(dtype)
     return out
+
+
+# ------------------------------------------------------------------------- env-sharded (multi-GPU) update
+def ppo_minibatch_grads(actor, critic, batch, hp, denominator=None):
+    """Unclipped gradient SUMS of one rank's share of a minibatch, divided by ``denominator`` (the GLOBAL batch
+    size), and this rank's share of the three logged scalars -- what ``b200rl_ppo_grads`` leaves in the flat
+    buffer.  Summing the outputs over ranks gives the gradients / scalars of reference AgentPPO.py:189-204 on the
+    union minibatch.  Nets are not modified."""
+    import copy
+    a2, c2 = copy.deepcopy(actor), copy.deepcopy(critic)
+    dt = batch["state"].dtype
+    local = batch["state"].shape[0]
+    denominator = local if denominator is None else denominator
+    hp_raw = dict(hp, clip_grad_norm=0.0, learning_rate=0.0)
+    scalars, grads = ppo_minibatch(a2, c2, new_adam_state(a2, True), new_adam_state(c2, False), batch, hp_raw)
+    scale = dt.type(local / denominator)  # ppo_minibatch averaged over the local samples
+    return tuple(s * float(scale) for s in scalars), [g * scale for g in grads["actor"]], [g * scale for g in grads["critic"]]
+
+
+def ppo_apply_grads(actor, critic, opt_a, opt_c, grads_actor, grads_critic, hp):
+    """clip_grad_norm_ + Adam on (all-reduced) gradients, per net -- what ``b200rl_ppo_apply`` does on every rank."""
+    ga, _ = clip_grads([g.copy() for g in grads_actor], hp["clip_grad_norm"])
+    gc, _ = clip_grads([g.copy() for g in grads_critic], hp["clip_grad_norm"])
+    pc = [p for pair in zip(critic["W"], critic["b"]) for p in pair]
+    mc = [p for pair in zip(opt_c["m_W"], opt_c["m_b"]) for p in pair]
+    vc = [p for pair in zip(opt_c["v_W"], opt_c["v_b"]) for p in pair]
+    opt_c["step"] = adam_step(pc, gc, mc, vc, opt_c["step"], hp["learning_rate"])
+    pa = [p for pair in zip(actor["W"], actor["b"]) for p in pair] + [actor["action_std_log"]]
+    ma = [p for pair in zip(opt_a["m_W"], opt_a["m_b"]) for p in pair] + [opt_a["m_std"]]
+    va = [p for pair in zip(opt_a["v_W"], opt_a["v_b"]) for p in pair] + [opt_a["v_std"]]
+    opt_a["step"] = adam_step(pa, ga, ma, va, opt_a["step"], hp["learning_rate"])
+
+
+def lattice_stat_sums(advantages, env_offset):
+    """(sum adv, sum and sum of squares over the [::4, ::4] lattice taken on the GLOBAL env index) of one env shard --
+    the three doubles ``b200rl_gae`` emits; all-reduced they give reference AgentPPO.py:149's mean / std."""
+    adv = advantages.astype(np.float64)
+    cols = (np.arange(adv.shape[1]) + env_offset) % 4 == 0
+    lat = adv[::4][:, cols]
+    return np.array([adv.sum(), lat.sum(), (lat ** 2).sum(), 0.0])
+
+
+def stats_from_sums(sums, count_all, count_lattice):
+    mean = sums[0] / count_all
+    m_lat = sums[1] / count_lattice
+    var = (sums[2] - count_lattice * m_lat * m_lat) / (count_lattice - 1.0)
+    return mean, math.sqrt(max(var, 0.0))
