@@ -194,10 +194,9 @@ def run_engine(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # returns after the first sample: nvidia-smi start-up is outside the timed region
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.4:   # same load while the sampler collects (short timed regions)
-        cycle_device()
-        th.cuda.synchronize()
+    for _ in range(150):         # ~0.4 s of the same load while the sampler collects (a fixed count: every rank
+        cycle_device()           # must issue the same number of collectives)
+    th.cuda.synchronize()
     launches0 = lib.b200rl_launch_count()
     ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     roll_events = []

@@ -45,7 +45,8 @@ int64_t b200rl_workspace_grad_offset(void) { return B200RL_WS_HEADER_BYTES; }
 int64_t b200rl_workspace_bytes(const b200rl_net* actor, const b200rl_net* critic) {
     int64_t n = b200rl_grad_numel(actor, critic);
     if (n < 0) return -1;
-    return B200RL_WS_HEADER_BYTES + ((n * 4 + 255) / 256) * 256;
+    const int64_t stride = (n + 63) & ~(int64_t)63;  // two gradient buffers (the persistent update kernel alternates)
+    return B200RL_WS_HEADER_BYTES + 2 * stride * 4;
 }
 
 }  // extern "C"

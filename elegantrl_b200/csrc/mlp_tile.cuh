@@ -38,8 +38,17 @@ DEV void load_state_tile(const b200rl_net& net, const float* __restrict__ x, int
 
 // Ys[j][b] = act(sum_k W[j][k] * Xs[k][b] + bias[j]); optionally Gs[j][b] = act'(pre-activation).
 // Thread tile: 4 samples x 4 outputs.  W is read through the read-only path (L1-resident: a few KB per layer).
-template <int TB, int NT>
-DEV void linear_forward(const float* __restrict__ W, const float* __restrict__ bias, int K, int J, const float* Xs,
+// parameter loads: read-only (non-coherent) path for kernels that only read the parameters; L2-coherent loads
+// (ld.global.cg) for the persistent update kernel, where other CTAs rewrite them between minibatches
+template <bool COHERENT>
+DEV float ldw(const float* p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+template <bool COHERENT>
+DEV float4 ldw4(const float* p) {
+    return COHERENT ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+}
+
+template <int TB, int NT, bool COHERENT = false>
+DEV void linear_forward(const float* W, const float* bias, int K, int J, const float* Xs,
                         float* Ys, float* Gs, int act, bool apply_act) {
     constexpr int NSG = TB / 4, NOL = NT / NSG;
     using T = SmemTile<TB>;
@@ -49,7 +58,7 @@ DEV void linear_forward(const float* __restrict__ W, const float* __restrict__ b
         float acc[4][4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-            float bv = (j0 + jj < J) ? __ldg(bias + j0 + jj) : 0.0f;
+            float bv = (j0 + jj < J) ? ldw<COHERENT>(bias + j0 + jj) : 0.0f;
 #pragma unroll
             for (int s = 0; s < 4; ++s) acc[jj][s] = bv;
         }
@@ -61,7 +70,7 @@ DEV void linear_forward(const float* __restrict__ W, const float* __restrict__ b
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (j0 + jj < J) {
-                        float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)(j0 + jj) * K + k));
+                        float4 w = ldw4<COHERENT>(W + (size_t)(j0 + jj) * K + k);
                         acc[jj][0] = fmaf(w.x, xv[0].x, acc[jj][0]); acc[jj][1] = fmaf(w.x, xv[0].y, acc[jj][1]);
                         acc[jj][2] = fmaf(w.x, xv[0].z, acc[jj][2]); acc[jj][3] = fmaf(w.x, xv[0].w, acc[jj][3]);
                         acc[jj][0] = fmaf(w.y, xv[1].x, acc[jj][0]); acc[jj][1] = fmaf(w.y, xv[1].y, acc[jj][1]);
@@ -79,7 +88,7 @@ DEV void linear_forward(const float* __restrict__ W, const float* __restrict__ b
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (j0 + jj < J) {
-                        float w = __ldg(W + (size_t)(j0 + jj) * K + k);
+                        float w = ldw<COHERENT>(W + (size_t)(j0 + jj) * K + k);
                         acc[jj][0] = fmaf(w, xv.x, acc[jj][0]); acc[jj][1] = fmaf(w, xv.y, acc[jj][1]);
                         acc[jj][2] = fmaf(w, xv.z, acc[jj][2]); acc[jj][3] = fmaf(w, xv.w, acc[jj][3]);
                     }

@@ -10,7 +10,13 @@
 // ("last block done") computes the two grad norms, clips, applies Adam in place on the caller's parameter /
 // moment tensors, and re-zeroes the buffer for the next minibatch.  Sharded (multi-GPU) callers stop after the
 // gradient phase (b200rl_ppo_grads), all-reduce the flat buffer, then run b200rl_ppo_apply.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "mlp_tile.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -40,6 +46,9 @@ struct UpdateArgs {
     int fused_apply;
     int smem_scalar_off;       // float offset of the per-sample scalar block in dynamic smem
     int maxdim;
+    int update_times;          // persistent (cluster) kernel: minibatches per launch
+    int grad_stride;           // floats between the two gradient buffers of the persistent kernel
+    float* out_scalars;        // persistent kernel: means of the three logged scalars
 };
 
 // dW[j][k] += sum_b dZ[j][b] * X[k][b];  db[j] += sum_b dZ[j][b]      (RED.ADD into the flat buffer)
@@ -88,6 +97,7 @@ DEV void weight_grad(const float* dZ, const float* X, int J, int K, float* gW, f
 }
 
 // dZprev[k][b] = (sum_j W[j][k] * dZ[j][b]) * G[k][b]
+template <bool COHERENT>
 DEV void data_grad(const float* W, const float* dZ, const float* G, float* dZprev, int J, int K) {
     constexpr int NSG = UTB / 4, NOL = kUpdThreads / NSG;
     const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
@@ -102,11 +112,11 @@ DEV void data_grad(const float* W, const float* dZ, const float* G, float* dZpre
             float4 dz = ld4(dZ + UT::chunk(j, sg));
             float w[4];
             if (vec) {
-                float4 w4 = *reinterpret_cast<const float4*>(W + (size_t)j * K + k0);
+                float4 w4 = ldw4<COHERENT>(W + (size_t)j * K + k0);
                 w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
             } else {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) w[kk] = (k0 + kk < K) ? W[(size_t)j * K + k0 + kk] : 0.0f;
+                for (int kk = 0; kk < 4; ++kk) w[kk] = (k0 + kk < K) ? ldw<COHERENT>(W + (size_t)j * K + k0 + kk) : 0.0f;
             }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -144,9 +154,10 @@ DEV void adam_one(float& p, float& m, float& v, float g, float b1, float b2, flo
     p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-as.step_size, m), denom));         // addcdiv_(exp_avg, denom, -step_size)
 }
 
-// clip_grad_norm_ + Adam.step for one net, executed by one whole CTA.
+// clip_grad_norm_ + Adam.step for one net.  The whole CTA computes the norm of the net's gradient; it then updates
+// the part `part` of `nparts` of every tensor (nparts = 1: the whole net; > 1: the CTAs of a cluster share the net).
 DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
-                   float clip_grad_norm, float* red) {
+                   float clip_grad_norm, float* red, int part = 0, int nparts = 1) {
     float ss = 0.0f;
     for (int i = threadIdx.x; i < numel; i += kUpdThreads) {
         float v = __ldcg(g + i);
@@ -158,6 +169,7 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
     const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps;
     int off = 0;
     const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
+    const int first = part * kUpdThreads + threadIdx.x, stride = nparts * kUpdThreads;
     for (int ti = 0; ti < n_tensors; ++ti) {
         float *p, *m, *v;
         int count;
@@ -175,8 +187,8 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
         if (vec) {  // 128-bit path: four independent parameter lanes per thread and iteration
             const float4* g4 = reinterpret_cast<const float4*>(g + off);
             float4 *p4 = reinterpret_cast<float4*>(p), *m4 = reinterpret_cast<float4*>(m), *v4 = reinterpret_cast<float4*>(v);
-            for (int i = threadIdx.x; i < (count >> 2); i += kUpdThreads) {
-                float4 gg = __ldcg(g4 + i), pp = p4[i], mm = m4[i], vv = v4[i];
+            for (int i = first; i < (count >> 2); i += stride) {
+                float4 gg = __ldcg(g4 + i), pp = __ldcg(p4 + i), mm = __ldcg(m4 + i), vv = __ldcg(v4 + i);
                 adam_one(pp.x, mm.x, vv.x, gg.x * coef, b1, b2, eps, as);
                 adam_one(pp.y, mm.y, vv.y, gg.y * coef, b1, b2, eps, as);
                 adam_one(pp.z, mm.z, vv.z, gg.z * coef, b1, b2, eps, as);
@@ -184,8 +196,8 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
                 p4[i] = pp; m4[i] = mm; v4[i] = vv;
             }
         } else {
-            for (int i = threadIdx.x; i < count; i += kUpdThreads) {
-                float pi = p[i], mi = m[i], vi = v[i];
+            for (int i = first; i < count; i += stride) {
+                float pi = __ldcg(p + i), mi = __ldcg(m + i), vi = __ldcg(v + i);
                 adam_one(pi, mi, vi, __ldcg(g + off + i) * coef, b1, b2, eps, as);
                 p[i] = pi; m[i] = mi; v[i] = vi;
             }
@@ -194,15 +206,13 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
     }
 }
 
-__global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_constant__ UpdateArgs A) {
-    extern __shared__ float4 smem4[];
-    float* smem = reinterpret_cast<float*>(smem4);
-    __shared__ float red[32];
-    __shared__ int64_t s_tn[UTB];  // t * N + n of each sample
-    __shared__ int s_last;
-
+// Gradient phase of one (sample tile, net): gather -> forward -> loss -> backward, RED.ADD into `grads` (flat buffer
+// of BOTH nets), loss sums into A.loss_sums.  COHERENT selects L2-coherent parameter loads (persistent kernel).
+template <bool COHERENT>
+DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, uint64_t draw, float* grads, float* smem,
+                     int64_t* s_tn) {
     const int H = A.buf.horizon_len, N = A.buf.num_envs;
-    const int slot0 = blockIdx.x * UTB;
+    const int slot0 = tile * UTB;
     float* sc = smem + A.smem_scalar_off;  // per-sample scalars
     float* s_unmask = sc, *s_logp = sc + UTB, *s_adv = sc + 2 * UTB, *s_rsum = sc + 3 * UTB, *s_act = sc + 4 * UTB;
 
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
         int64_t tn = -1;
         float um = 0.f, lp = 0.f, adv = 0.f, rs = 0.f;
         if (slot < A.local_batch) {
-            int64_t id = A.ids ? A.ids[slot] : sample_index(A.seed, A.draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+            int64_t id = ids ? ids[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
             int64_t t = id % H, n = id / H;
             tn = t * N + n;
             um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
@@ -234,104 +244,112 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     const float inv_bsz = 1.0f / (float)A.global_batch;
     float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;  // valid in threads < UTB
 
-    // ---- blockIdx.y selects the net: the critic and actor updates are disjoint (reference :189-204 steps the critic
-    //      first, but neither net reads the other's parameters), so they run as concurrent CTAs
-    const int ni = blockIdx.y;
-    {
-        const b200rl_net& net = A.net[ni];
-        const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
-        // smem map: X[0..L-1] (inputs of each Linear), G[1..L-1] (act' at each hidden layer), dzA, dzB
-        int xoff[B200RL_MAX_LINEAR + 1], goff[B200RL_MAX_LINEAR + 1];
-        int off = 0;
-        for (int l = 0; l < L; ++l) { xoff[l] = off; off += net.dims[l] * UTB; }
-        for (int l = 1; l < L; ++l) { goff[l] = off; off += net.dims[l] * UTB; }
-        float* dzA = smem + off;
-        float* dzB = dzA + A.maxdim * UTB;
+    const b200rl_net& net = A.net[ni];
+    const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
+    // smem map: X[0..L-1] (inputs of each Linear), G[1..L-1] (act' at each hidden layer), dzA, dzB
+    int xoff[B200RL_MAX_LINEAR + 1], goff[B200RL_MAX_LINEAR + 1];
+    int off = 0;
+    for (int l = 0; l < L; ++l) { xoff[l] = off; off += net.dims[l] * UTB; }
+    for (int l = 1; l < L; ++l) { goff[l] = off; off += net.dims[l] * UTB; }
+    float* dzA = smem + off;
+    float* dzB = dzA + A.maxdim * UTB;
 
-        // gather + state_norm into X[0]
-        for (int idx = threadIdx.x; idx < UTB * S; idx += kUpdThreads) {
-            int b = idx / S, k = idx - b * S;
-            float v = 0.0f;
-            if (s_tn[b] >= 0) {
-                v = A.buf.states[s_tn[b] * S + k];
-                if (net.state_avg) v = (v - net.state_avg[k]) / (net.state_std[k] + 1e-4f);
-            }
-            smem[xoff[0] + UT::elem(k, b)] = v;
+    // gather + state_norm into X[0]
+    for (int idx = threadIdx.x; idx < UTB * S; idx += kUpdThreads) {
+        int b = idx / S, k = idx - b * S;
+        float v = 0.0f;
+        if (s_tn[b] >= 0) {
+            v = A.buf.states[s_tn[b] * S + k];
+            if (net.state_avg) v = (v - net.state_avg[k]) / (net.state_std[k] + 1e-4f);
         }
+        smem[xoff[0] + UT::elem(k, b)] = v;
+    }
+    __syncthreads();
+    // forward, keeping every layer input and act'
+    for (int l = 0; l < L; ++l) {
+        const bool hidden = l < L - 1;
+        linear_forward<UTB, kUpdThreads, COHERENT>(net.weight[l], net.bias[l], net.dims[l], net.dims[l + 1], smem + xoff[l],
+                                                   hidden ? smem + xoff[l + 1] : dzA, hidden ? smem + goff[l + 1] : nullptr,
+                                                   net.activation, hidden);
         __syncthreads();
-        // forward, keeping every layer input and act'
-        for (int l = 0; l < L; ++l) {
-            const bool hidden = l < L - 1;
-            linear_forward<UTB, kUpdThreads>(net.weight[l], net.bias[l], net.dims[l], net.dims[l + 1], smem + xoff[l],
-                                             hidden ? smem + xoff[l + 1] : dzA, hidden ? smem + goff[l + 1] : nullptr,
-                                             net.activation, hidden);
-            __syncthreads();
-        }
-        // loss and d loss / d output, in place in dzA
-        float* g = A.grads + A.grad_off[ni];
-        if (threadIdx.x < UTB) {
-            const int b = threadIdx.x;
-            const bool valid = s_tn[b] >= 0;
-            const float um = s_unmask[b];
-            if (ni == 1) {
-                // obj_critic = mean(MSE(V(s), reward_sum) * unmask)          (:189-190)
-                float err = dzA[UT::elem(0, b)] - s_rsum[b];
-                loss_c = valid ? err * err * um : 0.0f;
-                dzA[UT::elem(0, b)] = valid ? 2.0f * err * um * inv_bsz : 0.0f;
-            } else {
-                // new_logprob, ratio, "clip" factor, entropy                 (:193-203)
-                float logp = 0.0f, ent = 0.0f;
-                for (int a = 0; a < OUT; ++a) {
-                    float sd = expf(net.action_std_log[a]);
-                    float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
-                    float lsd = logf(sd);
-                    logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
-                    ent += 0.5f + kLogSqrt2Pi + lsd;  // 0.5 + 0.5 log(2 pi) + log(scale)
-                }
-                float ratio = expf(logp - s_logp[b]);
-                float adv = s_adv[b];
-                float kappa = adv > 0.0f ? 1.0f - A.hp.ratio_clip : 1.0f + A.hp.ratio_clip;
-                float surr = adv * ratio * kappa;
-                loss_s = valid ? surr * um : 0.0f;
-                loss_e = valid ? ent * um : 0.0f;
-                // loss = -(obj_surrogate - lambda_entropy * obj_entropy)
-                float gl = valid ? -(surr * um) * inv_bsz : 0.0f;
-                for (int a = 0; a < OUT; ++a) {
-                    float sd = expf(net.action_std_log[a]);
-                    float var = sd * sd;
-                    float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
-                    dzA[UT::elem(a, b)] = gl * diff / var;
-                    float dstd = gl * (diff * diff / var - 1.0f) + (valid ? A.hp.lambda_entropy * um * inv_bsz : 0.0f);
-                    dstd = warp_sum(dstd);  // UTB == 32: exactly warp 0
-                    if (b == 0) atomicAdd(g + A.grad_numel[0] - OUT + a, dstd);
-                }
+    }
+    // loss and d loss / d output, in place in dzA
+    float* g = grads + A.grad_off[ni];
+    if (threadIdx.x < UTB) {
+        const int b = threadIdx.x;
+        const bool valid = s_tn[b] >= 0;
+        const float um = s_unmask[b];
+        if (ni == 1) {
+            // obj_critic = mean(MSE(V(s), reward_sum) * unmask)          (:189-190)
+            float err = dzA[UT::elem(0, b)] - s_rsum[b];
+            loss_c = valid ? err * err * um : 0.0f;
+            dzA[UT::elem(0, b)] = valid ? 2.0f * err * um * inv_bsz : 0.0f;
+        } else {
+            // new_logprob, ratio, "clip" factor, entropy                 (:193-203)
+            float logp = 0.0f, ent = 0.0f;
+            for (int a = 0; a < OUT; ++a) {
+                float sd = expf(ldw<COHERENT>(net.action_std_log + a));
+                float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
+                float lsd = logf(sd);
+                logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
+                ent += 0.5f + kLogSqrt2Pi + lsd;  // 0.5 + 0.5 log(2 pi) + log(scale)
+            }
+            float ratio = expf(logp - s_logp[b]);
+            float adv = s_adv[b];
+            float kappa = adv > 0.0f ? 1.0f - A.hp.ratio_clip : 1.0f + A.hp.ratio_clip;
+            float surr = adv * ratio * kappa;
+            loss_s = valid ? surr * um : 0.0f;
+            loss_e = valid ? ent * um : 0.0f;
+            // loss = -(obj_surrogate - lambda_entropy * obj_entropy)
+            float gl = valid ? -(surr * um) * inv_bsz : 0.0f;
+            for (int a = 0; a < OUT; ++a) {
+                float sd = expf(ldw<COHERENT>(net.action_std_log + a));
+                float var = sd * sd;
+                float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
+                dzA[UT::elem(a, b)] = gl * diff / var;
+                float dstd = gl * (diff * diff / var - 1.0f) + (valid ? A.hp.lambda_entropy * um * inv_bsz : 0.0f);
+                dstd = warp_sum(dstd);  // UTB == 32: exactly warp 0
+                if (b == 0) atomicAdd(g + A.grad_numel[0] - OUT + a, dstd);
             }
         }
+    }
+    __syncthreads();
+    // backward
+    float* dz = dzA;
+    float* dzn = dzB;
+    int goff_w = 0;  // float offset of W_l inside this net's flat gradient
+    int woff[B200RL_MAX_LINEAR];
+    for (int l = 0; l < L; ++l) { woff[l] = goff_w; goff_w += net.dims[l + 1] * net.dims[l] + net.dims[l + 1]; }
+    for (int l = L - 1; l >= 0; --l) {
+        const int J = net.dims[l + 1], K = net.dims[l];
+        weight_grad(dz, smem + xoff[l], J, K, g + woff[l], g + woff[l] + J * K);
+        if (l > 0) data_grad<COHERENT>(net.weight[l], dz, smem + goff[l], dzn, J, K);
         __syncthreads();
-        // backward
-        float* dz = dzA;
-        float* dzn = dzB;
-        int goff_w = 0;  // float offset of W_l inside this net's flat gradient
-        int woff[B200RL_MAX_LINEAR];
-        for (int l = 0; l < L; ++l) { woff[l] = goff_w; goff_w += net.dims[l + 1] * net.dims[l] + net.dims[l + 1]; }
-        for (int l = L - 1; l >= 0; --l) {
-            const int J = net.dims[l + 1], K = net.dims[l];
-            weight_grad(dz, smem + xoff[l], J, K, g + woff[l], g + woff[l] + J * K);
-            if (l > 0) data_grad(net.weight[l], dz, smem + goff[l], dzn, J, K);
-            __syncthreads();
-            float* t = dz; dz = dzn; dzn = t;
-        }
+        float* t = dz; dz = dzn; dzn = t;
     }
 
     // ---- loss sums (means over the global batch) -> double accumulators
     if (threadIdx.x < 32) {
         float c = warp_sum(loss_c), s = warp_sum(loss_s), e = warp_sum(loss_e);
         if (threadIdx.x == 0) {
-            atomicAdd(A.loss_sums + 0, (double)(c * inv_bsz));
-            atomicAdd(A.loss_sums + 1, (double)(s * inv_bsz));
-            atomicAdd(A.loss_sums + 2, (double)(e * inv_bsz));
+            if (ni == 1) atomicAdd(A.loss_sums + 0, (double)(c * inv_bsz));
+            else {
+                atomicAdd(A.loss_sums + 1, (double)(s * inv_bsz));
+                atomicAdd(A.loss_sums + 2, (double)(e * inv_bsz));
+            }
         }
     }
+}
+
+// one launch per minibatch: grid = (sample tiles, 2 nets); last-block-done apply per net
+__global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_constant__ UpdateArgs A) {
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
+    __shared__ float red[32];
+    __shared__ int64_t s_tn[UTB];  // t * N + n of each sample
+    __shared__ int s_last;
+    const int ni = blockIdx.y;  // the critic and actor updates are disjoint (reference :189-204): concurrent CTAs
+    grads_phase<false>(A, blockIdx.x, ni, A.ids, A.draw, A.grads, smem, s_tn);
     if (!A.fused_apply) return;
 
     // ---- last block done (per net): clip + Adam for this net, then re-zero its slice of the gradient buffer
@@ -345,6 +363,41 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     __syncthreads();
     for (int i = threadIdx.x; i < A.grad_numel[ni]; i += kUpdThreads) A.grads[A.grad_off[ni] + i] = 0.0f;
     if (threadIdx.x == 0) A.hdr->ticket[ni] = 0u;
+}
+
+// ALL minibatches of one update_net in ONE launch: the grid is a single thread-block cluster (2 nets x sample tiles
+// <= 8 CTAs), minibatches are separated by hardware cluster barriers instead of kernel boundaries, the clip + Adam of
+// each net is shared by that net's CTAs, gradient buffers alternate so that re-zeroing overlaps the next minibatch.
+__global__ void __launch_bounds__(kUpdThreads) ppo_update_cluster_kernel(const __grid_constant__ UpdateArgs A) {
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
+    __shared__ float red[32];
+    __shared__ int64_t s_tn[UTB];
+    __shared__ AdamScalars s_adam;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tiles = gridDim.x >> 1;
+    const int ni = blockIdx.x / tiles, tile = blockIdx.x - ni * tiles;
+    const int gtotal = A.grad_off[1] + A.grad_numel[1];
+
+    for (int u = 0; u < A.update_times; ++u) {
+        float* gcur = A.grads + (u & 1) * A.grad_stride;
+        float* gnext = A.grads + ((u + 1) & 1) * A.grad_stride;
+        if (threadIdx.x == 0) {  // torch.optim.Adam bias corrections of this step, in double like torch
+            const double step = (double)(A.opt[ni].step + u + 1);
+            s_adam.step_size = (float)((double)A.opt[ni].lr / (1.0 - pow((double)A.opt[ni].beta1, step)));
+            s_adam.bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
+        }
+        grads_phase<true>(A, tile, ni, A.ids ? A.ids + (size_t)u * A.local_batch : nullptr, A.draw + (uint64_t)u, gcur, smem, s_tn);
+        __threadfence();
+        cluster.sync();
+        // this net's CTAs share its clip + Adam; they also re-zero the other gradient buffer for minibatch u + 1
+        apply_net(A.net[ni], A.opt[ni], s_adam, gcur + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red, tile, tiles);
+        for (int i = blockIdx.x * kUpdThreads + threadIdx.x; i < gtotal; i += gridDim.x * kUpdThreads) gnext[i] = 0.0f;
+        __threadfence();
+        cluster.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 3)
+        A.out_scalars[threadIdx.x] = (float)(__ldcg(A.loss_sums + threadIdx.x) / (double)A.update_times);
 }
 
 __global__ void __launch_bounds__(kUpdThreads) ppo_apply_kernel(const __grid_constant__ UpdateArgs A) {
@@ -435,19 +488,46 @@ int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* critic, b200rl_
     A.fused_apply = 1;
     A.local_batch = A.global_batch = batch_size;
     A.seed = seed;
-    B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200RL_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)b200rl_workspace_bytes(actor, critic), stream));
-    const dim3 grid((unsigned)((batch_size + UTB - 1) / UTB), 2);
-    for (int u = 0; u < update_times; ++u) {
-        A.ids = ids ? ids + (size_t)u * batch_size : nullptr;
-        A.draw = draw_offset + (uint64_t)u;
-        A.adam[0] = adam_scalars(actor_opt, actor_opt->step + u + 1);
-        A.adam[1] = adam_scalars(critic_opt, critic_opt->step + u + 1);
-        ppo_grads_kernel<<<grid, kUpdThreads, smem, stream>>>(A);
+    const int tiles = (batch_size + UTB - 1) / UTB;
+    const char* mode = getenv("B200RL_UPDATE");
+    const bool want_multi = mode && strcmp(mode, "multilaunch") == 0;
+    if (2 * tiles <= 8 && !want_multi) {
+        // small minibatches (the Config default 128): the whole update_net loop as ONE persistent cluster launch
+        A.update_times = update_times;
+        A.grad_stride = (int)((b200rl_grad_numel(actor, critic) + 63) & ~(int64_t)63);
+        A.out_scalars = out_scalars;
+        A.ids = ids;
+        A.draw = draw_offset;
+        B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_update_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * tiles);
+        cfg.blockDim = dim3(kUpdThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2 * tiles;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B200RL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ppo_update_cluster_kernel, A));
+        B200RL_COUNT_LAUNCH(1);
+    } else {
+        B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const dim3 grid((unsigned)tiles, 2);
+        for (int u = 0; u < update_times; ++u) {
+            A.ids = ids ? ids + (size_t)u * batch_size : nullptr;
+            A.draw = draw_offset + (uint64_t)u;
+            A.adam[0] = adam_scalars(actor_opt, actor_opt->step + u + 1);
+            A.adam[1] = adam_scalars(critic_opt, critic_opt->step + u + 1);
+            ppo_grads_kernel<<<grid, kUpdThreads, smem, stream>>>(A);
+        }
+        B200RL_COUNT_LAUNCH(update_times + 1);
+        B200RL_CHECK_CUDA(cudaGetLastError());
+        loss_means_kernel<<<1, 32, 0, stream>>>(A.loss_sums, 1.0 / (double)update_times, out_scalars);
     }
-    B200RL_COUNT_LAUNCH(update_times + 1);
-    B200RL_CHECK_CUDA(cudaGetLastError());
-    loss_means_kernel<<<1, 32, 0, stream>>>(A.loss_sums, 1.0 / (double)update_times, out_scalars);
     B200RL_CHECK_CUDA(cudaGetLastError());
     actor_opt->step += update_times;
     critic_opt->step += update_times;

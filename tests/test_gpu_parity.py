@@ -165,6 +165,14 @@ def test_gae_sizes_against_oracle(shape, v_trace):
 
 
 # ----------------------------------------------------------------------------------------- update
+@pytest.fixture(params=["cluster", "multilaunch"])
+def update_impl(request, monkeypatch):
+    """Both update drivers: one persistent thread-block-cluster launch for all minibatches, and one launch per
+    minibatch (what large batches use)."""
+    monkeypatch.setenv("B200RL_UPDATE", request.param)
+    return request.param
+
+
 def _adam_tensors(agent, which):
     module, opt = (agent.act, agent.act_optimizer) if which == "actor" else (agent.cri, agent.cri_optimizer)
     from elegantrl_b200.agents.AgentPPO import _trainable
@@ -193,7 +201,7 @@ def _run_ppo_update(agent, buffer, ids, pre_normalised=True, stats=None):
 
 
 @pytest.mark.parametrize("case", gu.SYNTH_CASES)
-def test_update_objectives_against_reference(case):
+def test_update_objectives_against_reference(case, update_impl):
     g = gu.load(case)
     buffer = [G.cuda(g[k]) for k in ("buf.states", "buf.actions", "buf.unmasks", "buf.logprobs", "gae.adv_norm", "gae.reward_sums")]
     ids = G.cuda(g["update.ids"])
@@ -233,7 +241,7 @@ def test_update_gather_time_normalisation_equals_prenormalised(case):
 
 
 @pytest.mark.parametrize("case", gu.SYNTH_CASES + gu.ROLLOUT_CASES)
-def test_update_net_against_reference(case):
+def test_update_net_against_reference(case, update_impl):
     g = gu.load(case)
     agent = G.agent_from_golden(g)
     src = "buf" if "buf.states" in g else "rollout"
