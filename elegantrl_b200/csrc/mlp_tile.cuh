@@ -36,33 +36,79 @@ DEV void load_state_tile(const b200rl_net& net, const float* __restrict__ x, int
     }
 }
 
-// Ys[j][b] = act(sum_k W[j][k] * Xs[k][b] + bias[j]); optionally Gs[j][b] = act'(pre-activation).
-// Thread tile: 4 samples x 4 outputs.  W is read through the read-only path (L1-resident: a few KB per layer).
-// parameter loads: read-only (non-coherent) path for kernels that only read the parameters; L2-coherent loads
-// (ld.global.cg) for the persistent update kernel, where other CTAs rewrite them between minibatches
-template <bool COHERENT>
-DEV float ldw(const float* p) { return COHERENT ? __ldcg(p) : __ldg(p); }
-template <bool COHERENT>
-DEV float4 ldw4(const float* p) {
-    return COHERENT ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+// ---- where a Linear's parameters are read from
+//  W_LDG   global memory, read-only (non-coherent) path: kernels that only read the parameters
+//  W_LDCG  global memory, L2-coherent loads: parameters rewritten by other CTAs during the kernel
+//  W_SMEM  a copy staged in shared memory by stage_weight(): rows of K floats whose 16-byte chunks are XOR-swizzled
+//          by the row's 4-row group (when K % 32 == 0), so that both "4 consecutive rows, same k" (forward) and
+//          "same row, 4 consecutive k-chunks per lane group" (data gradient) are bank-conflict free
+enum WeightMode { W_LDG = 0, W_LDCG = 1, W_SMEM = 2 };
+
+template <int WM>
+struct WeightView {
+    const float* base;
+    int K;
+    bool vec;   // float4 access legal (K % 4 == 0 and aligned)
+    bool swz;   // W_SMEM only: swizzled rows
+    DEV WeightView(const float* b, int k) : base(b), K(k) {
+        vec = ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+        swz = (WM == W_SMEM) && ((k & 31) == 0);
+    }
+    DEV int off4(int j, int k) const {  // float offset of the 16-byte chunk holding (j, k..k+3), k % 4 == 0
+        return swz ? j * K + ((((k >> 2) ^ (j >> 2)) & 7) << 2) + ((k >> 5) << 5) : j * K + k;
+    }
+    DEV float4 ld4(int j, int k) const {
+        const float* p = base + off4(j, k);
+        if (WM == W_LDG) return __ldg(reinterpret_cast<const float4*>(p));
+        if (WM == W_LDCG) return __ldcg(reinterpret_cast<const float4*>(p));
+        return *reinterpret_cast<const float4*>(p);
+    }
+    DEV float ld1(int j, int k) const {
+        const float* p = base + (swz ? off4(j, k & ~3) + (k & 3) : j * K + k);
+        if (WM == W_LDG) return __ldg(p);
+        if (WM == W_LDCG) return __ldcg(p);
+        return *p;
+    }
+};
+template <int WM>
+DEV float ld_param(const float* p) { return WM == W_LDG ? __ldg(p) : (WM == W_LDCG ? __ldcg(p) : *p); }
+
+// copy W [J][K] (global, coherent loads) into the shared-memory layout WeightView<W_SMEM> reads
+template <int NT>
+DEV void stage_weight(const float* __restrict__ W, int J, int K, float* dst) {
+    const bool swz = (K & 31) == 0;
+    if (((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0)) {
+        const int chunks = K >> 2;
+        for (int i = threadIdx.x; i < J * chunks; i += NT) {
+            const int j = i / chunks, c = i - j * chunks;
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(W) + i);
+            const int cs = swz ? ((c & ~7) | ((c ^ (j >> 2)) & 7)) : c;
+            *reinterpret_cast<float4*>(dst + j * K + (cs << 2)) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < J * K; i += NT) dst[i] = __ldcg(W + i);
+    }
 }
 
-template <int TB, int NT, bool COHERENT = false>
-DEV void linear_forward(const float* W, const float* bias, int K, int J, const float* Xs,
-                        float* Ys, float* Gs, int act, bool apply_act) {
+// Ys[j][b] = act(sum_k W[j][k] * Xs[k][b] + bias[j]); optionally Gs[j][b] = act'(pre-activation).
+// Thread tile: 4 samples x 4 outputs.
+template <int TB, int NT, int WM = W_LDG>
+DEV void linear_forward(const float* Wp, const float* bias, int K, int J, const float* Xs, float* Ys, float* Gs, int act,
+                        bool apply_act) {
     constexpr int NSG = TB / 4, NOL = NT / NSG;
     using T = SmemTile<TB>;
     const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
-    const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    const WeightView<WM> W(Wp, K);
     for (int j0 = ol * 4; j0 < J; j0 += NOL * 4) {
         float acc[4][4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-            float bv = (j0 + jj < J) ? ldw<COHERENT>(bias + j0 + jj) : 0.0f;
+            float bv = (j0 + jj < J) ? ld_param<WM>(bias + j0 + jj) : 0.0f;
 #pragma unroll
             for (int s = 0; s < 4; ++s) acc[jj][s] = bv;
         }
-        if (vec) {
+        if (W.vec) {
+#pragma unroll 2
             for (int k = 0; k < K; k += 4) {
                 float4 xv[4];
 #pragma unroll
@@ -70,7 +116,7 @@ DEV void linear_forward(const float* W, const float* bias, int K, int J, const f
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (j0 + jj < J) {
-                        float4 w = ldw4<COHERENT>(W + (size_t)(j0 + jj) * K + k);
+                        float4 w = W.ld4(j0 + jj, k);
                         acc[jj][0] = fmaf(w.x, xv[0].x, acc[jj][0]); acc[jj][1] = fmaf(w.x, xv[0].y, acc[jj][1]);
                         acc[jj][2] = fmaf(w.x, xv[0].z, acc[jj][2]); acc[jj][3] = fmaf(w.x, xv[0].w, acc[jj][3]);
                         acc[jj][0] = fmaf(w.y, xv[1].x, acc[jj][0]); acc[jj][1] = fmaf(w.y, xv[1].y, acc[jj][1]);
@@ -88,7 +134,7 @@ DEV void linear_forward(const float* W, const float* bias, int K, int J, const f
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (j0 + jj < J) {
-                        float w = ldw<COHERENT>(W + (size_t)(j0 + jj) * K + k);
+                        float w = W.ld1(j0 + jj, k);
                         acc[jj][0] = fmaf(w, xv.x, acc[jj][0]); acc[jj][1] = fmaf(w, xv.y, acc[jj][1]);
                         acc[jj][2] = fmaf(w, xv.z, acc[jj][2]); acc[jj][3] = fmaf(w, xv.w, acc[jj][3]);
                     }

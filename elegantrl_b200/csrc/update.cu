@@ -46,6 +46,8 @@ struct UpdateArgs {
     int fused_apply;
     int smem_scalar_off;       // float offset of the per-sample scalar block in dynamic smem
     int maxdim;
+    int stage_weights;         // parameters of the net fit in shared memory: stage them per minibatch
+    int smem_weight_off;       // float offset of the staged parameters in dynamic smem
     int update_times;          // persistent (cluster) kernel: minibatches per launch
     int grad_stride;           // floats between the two gradient buffers of the persistent kernel
     float* out_scalars;        // persistent kernel: means of the three logged scalars
@@ -97,26 +99,28 @@ DEV void weight_grad(const float* dZ, const float* X, int J, int K, float* gW, f
 }
 
 // dZprev[k][b] = (sum_j W[j][k] * dZ[j][b]) * G[k][b]
-template <bool COHERENT>
-DEV void data_grad(const float* W, const float* dZ, const float* G, float* dZprev, int J, int K) {
+template <int WM>
+DEV void data_grad(const float* Wp, const float* dZ, const float* G, float* dZprev, int J, int K) {
     constexpr int NSG = UTB / 4, NOL = kUpdThreads / NSG;
     const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
-    const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    const WeightView<WM> W(Wp, K);
+    const bool vec = W.vec;
     for (int k0 = ol * 4; k0 < K; k0 += NOL * 4) {
         float acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+#pragma unroll 4
         for (int j = 0; j < J; ++j) {
             float4 dz = ld4(dZ + UT::chunk(j, sg));
             float w[4];
             if (vec) {
-                float4 w4 = ldw4<COHERENT>(W + (size_t)j * K + k0);
+                float4 w4 = W.ld4(j, k0);
                 w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
             } else {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) w[kk] = (k0 + kk < K) ? ldw<COHERENT>(W + (size_t)j * K + k0 + kk) : 0.0f;
+                for (int kk = 0; kk < 4; ++kk) w[kk] = (k0 + kk < K) ? W.ld1(j, k0 + kk) : 0.0f;
             }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -207,8 +211,9 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
 }
 
 // Gradient phase of one (sample tile, net): gather -> forward -> loss -> backward, RED.ADD into `grads` (flat buffer
-// of BOTH nets), loss sums into A.loss_sums.  COHERENT selects L2-coherent parameter loads (persistent kernel).
-template <bool COHERENT>
+// of BOTH nets), loss sums into A.loss_sums.  WM: where the parameters are read from (mlp_tile.cuh); with W_SMEM the
+// net's parameters are first staged into shared memory with coalesced L2-coherent loads (small nets).
+template <int WM>
 DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, uint64_t draw, float* grads, float* smem,
                      int64_t* s_tn) {
     const int H = A.buf.horizon_len, N = A.buf.num_envs;
@@ -246,6 +251,25 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
 
     const b200rl_net& net = A.net[ni];
     const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
+    const float* Wl[B200RL_MAX_LINEAR];
+    const float* bl[B200RL_MAX_LINEAR];
+    const float* std_log = net.action_std_log;
+    if (WM == W_SMEM) {
+        float* w = smem + A.smem_weight_off;
+        for (int l = 0; l < L; ++l) {
+            const int J = net.dims[l + 1], K = net.dims[l];
+            stage_weight<kUpdThreads>(net.weight[l], J, K, w);
+            Wl[l] = w; w += (J * K + 3) & ~3;
+            for (int i = threadIdx.x; i < J; i += kUpdThreads) w[i] = __ldcg(net.bias[l] + i);
+            bl[l] = w; w += (J + 3) & ~3;
+        }
+        if (net.action_std_log) {
+            for (int i = threadIdx.x; i < OUT; i += kUpdThreads) w[i] = __ldcg(net.action_std_log + i);
+            std_log = w;
+        }
+    } else {
+        for (int l = 0; l < L; ++l) { Wl[l] = net.weight[l]; bl[l] = net.bias[l]; }
+    }
     // smem map: X[0..L-1] (inputs of each Linear), G[1..L-1] (act' at each hidden layer), dzA, dzB
     int xoff[B200RL_MAX_LINEAR + 1], goff[B200RL_MAX_LINEAR + 1];
     int off = 0;
@@ -268,7 +292,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
     // forward, keeping every layer input and act'
     for (int l = 0; l < L; ++l) {
         const bool hidden = l < L - 1;
-        linear_forward<UTB, kUpdThreads, COHERENT>(net.weight[l], net.bias[l], net.dims[l], net.dims[l + 1], smem + xoff[l],
+        linear_forward<UTB, kUpdThreads, WM>(Wl[l], bl[l], net.dims[l], net.dims[l + 1], smem + xoff[l],
                                                    hidden ? smem + xoff[l + 1] : dzA, hidden ? smem + goff[l + 1] : nullptr,
                                                    net.activation, hidden);
         __syncthreads();
@@ -288,7 +312,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
             // new_logprob, ratio, "clip" factor, entropy                 (:193-203)
             float logp = 0.0f, ent = 0.0f;
             for (int a = 0; a < OUT; ++a) {
-                float sd = expf(ldw<COHERENT>(net.action_std_log + a));
+                float sd = expf(ld_param<WM>(std_log + a));
                 float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
                 float lsd = logf(sd);
                 logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
@@ -303,7 +327,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
             // loss = -(obj_surrogate - lambda_entropy * obj_entropy)
             float gl = valid ? -(surr * um) * inv_bsz : 0.0f;
             for (int a = 0; a < OUT; ++a) {
-                float sd = expf(ldw<COHERENT>(net.action_std_log + a));
+                float sd = expf(ld_param<WM>(std_log + a));
                 float var = sd * sd;
                 float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
                 dzA[UT::elem(a, b)] = gl * diff / var;
@@ -323,7 +347,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
     for (int l = L - 1; l >= 0; --l) {
         const int J = net.dims[l + 1], K = net.dims[l];
         weight_grad(dz, smem + xoff[l], J, K, g + woff[l], g + woff[l] + J * K);
-        if (l > 0) data_grad<COHERENT>(net.weight[l], dz, smem + goff[l], dzn, J, K);
+        if (l > 0) data_grad<WM>(Wl[l], dz, smem + goff[l], dzn, J, K);
         __syncthreads();
         float* t = dz; dz = dzn; dzn = t;
     }
@@ -349,7 +373,8 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     __shared__ int64_t s_tn[UTB];  // t * N + n of each sample
     __shared__ int s_last;
     const int ni = blockIdx.y;  // the critic and actor updates are disjoint (reference :189-204): concurrent CTAs
-    grads_phase<false>(A, blockIdx.x, ni, A.ids, A.draw, A.grads, smem, s_tn);
+    if (A.stage_weights) grads_phase<W_SMEM>(A, blockIdx.x, ni, A.ids, A.draw, A.grads, smem, s_tn);
+    else grads_phase<W_LDG>(A, blockIdx.x, ni, A.ids, A.draw, A.grads, smem, s_tn);
     if (!A.fused_apply) return;
 
     // ---- last block done (per net): clip + Adam for this net, then re-zero its slice of the gradient buffer
@@ -387,7 +412,9 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_update_cluster_kernel(const _
             s_adam.step_size = (float)((double)A.opt[ni].lr / (1.0 - pow((double)A.opt[ni].beta1, step)));
             s_adam.bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
         }
-        grads_phase<true>(A, tile, ni, A.ids ? A.ids + (size_t)u * A.local_batch : nullptr, A.draw + (uint64_t)u, gcur, smem, s_tn);
+        const int64_t* ids_u = A.ids ? A.ids + (size_t)u * A.local_batch : nullptr;
+        if (A.stage_weights) grads_phase<W_SMEM>(A, tile, ni, ids_u, A.draw + (uint64_t)u, gcur, smem, s_tn);
+        else grads_phase<W_LDCG>(A, tile, ni, ids_u, A.draw + (uint64_t)u, gcur, smem, s_tn);
         __threadfence();
         cluster.sync();
         // this net's CTAs share its clip + Adam; they also re-zero the other gradient buffer for minibatch u + 1
@@ -456,7 +483,18 @@ int fill_args(UpdateArgs& A, const b200rl_net* actor, const b200rl_net* critic, 
     A.maxdim = maxdim;
     A.smem_scalar_off = (rows + 2 * maxdim) * UTB;
     int scalars = (4 + actor->dims[actor->num_linear]) * UTB;
-    *smem_bytes = (size_t)(A.smem_scalar_off + scalars) * sizeof(float);
+    // small nets: + a shared-memory copy of the net's parameters (rows padded to 16 bytes)
+    int wfloats = 0;
+    for (int ni = 0; ni < 2; ++ni) {
+        const b200rl_net& n = A.net[ni];
+        int w = 0;
+        for (int l = 0; l < n.num_linear; ++l) w += ((n.dims[l + 1] * n.dims[l] + 3) & ~3) + ((n.dims[l + 1] + 3) & ~3);
+        w += (n.dims[n.num_linear] + 3) & ~3;
+        wfloats = w > wfloats ? w : wfloats;
+    }
+    A.smem_weight_off = (A.smem_scalar_off + scalars + 3) & ~3;
+    A.stage_weights = (wfloats <= 16 * 1024 && (size_t)(A.smem_weight_off + wfloats) * sizeof(float) <= 200 * 1024) ? 1 : 0;
+    *smem_bytes = (size_t)(A.stage_weights ? A.smem_weight_off + wfloats : A.smem_scalar_off + scalars) * sizeof(float);
     B200RL_REQUIRE(*smem_bytes <= 227 * 1024, "ppo: nets too wide for the update kernel (%zu B of shared memory needed)",
                    *smem_bytes);
     return 0;
