@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(os.path.dirname(HERE), "include", "b200rl.h"))
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("B200RL_EXTRA_NVCC_FLAGS", "").split()
 
     def compile_one(src):
         src_path = os.path.join(CSRC, src)

@@ -73,6 +73,8 @@ SIGNATURES = {
     "b200rl_ppo_update": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.POINTER(Adam), C.POINTER(Adam),
                                     C.POINTER(TrainBuffer), C.POINTER(PPOHyper), C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200rl_pack_minibatches": (C.c_int, [C.POINTER(TrainBuffer), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200rl_ppo_grads": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.POINTER(TrainBuffer), C.POINTER(PPOHyper),
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p]),

@@ -386,11 +386,45 @@ class AgentPPO:
         return out
 
     def _update_sharded(self, lib, act_desc, cri_desc, act_adam, cri_adam, tb, hp, update_times, ids, out, workspace):
-        """Env-sharded minibatches: local gradient sums -> one NCCL all-reduce of the flat buffer -> clip + Adam
-        replicated on every rank (identical parameters everywhere without a broadcast)."""
+        """Env-sharded update.  The minibatch indices do not depend on the parameters, so every rank packs ITS share
+        of ALL the minibatches of this update_net (update_times x batch_size/world sampled transitions, ~30 KB) in
+        one kernel, ONE all-gather exchanges them, and every rank then runs the same single-launch update on the
+        same global minibatches; a broadcast of the (36 KB) parameters + moments from rank 0 keeps the replicas
+        bit-identical (the gradient reduction uses floating-point RED.ADD, whose order is not deterministic).
+        2 latency-bound collectives per cycle instead of one all-reduce per minibatch."""
         import torch.distributed as dist
         assert self.batch_size % self._world == 0, "batch_size must divide over the ranks"
         local_batch = self.batch_size // self._world
+        if getattr(self, "sharded_mode", "gather") == "gather":
+            rec = ((self.state_dim + self.action_dim + 3) & ~3) + 4
+            send = th.empty((update_times * local_batch, rec), dtype=th.float32, device=self.device)
+            seed = self.seed + 0x9E3779B9 * (self._rank + 1)  # independent index streams per shard
+            _lib.check(lib.b200rl_pack_minibatches(C.byref(tb), self.state_dim, self.action_dim, local_batch, update_times,
+                                                   _lib.ptr(ids), seed, self._update_draws, _lib.ptr(send), self._stream()),
+                       "pack_minibatches")
+            recv = th.empty((self._world * update_times * local_batch, rec), dtype=th.float32, device=self.device)
+            dist.all_gather_into_tensor(recv, send, group=self._dist_group)
+            key = (self._world, update_times, local_batch)
+            if getattr(self, "_packed_ids_key", None) != key:  # minibatch u = records (r, u, :) of every rank r
+                r = th.arange(self._world, device=self.device).view(1, -1, 1) * (update_times * local_batch)
+                u = th.arange(update_times, device=self.device).view(-1, 1, 1) * local_batch
+                j = th.arange(local_batch, device=self.device).view(1, 1, -1)
+                self._packed_ids = (r + u + j).reshape(update_times, -1).contiguous()
+                self._packed_ids_key = key
+            packed = _lib.TrainBuffer(states=_lib.ptr(recv), horizon_len=0, num_envs=recv.shape[0])
+            _lib.check(lib.b200rl_ppo_update(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam),
+                                             C.byref(packed), C.byref(hp), self.batch_size, update_times,
+                                             _lib.ptr(self._packed_ids), self.seed, self._update_draws, _lib.ptr(out),
+                                             _lib.ptr(workspace), workspace.numel(), self._stream()), "ppo_update")
+            tensors = [p.data for p in _trainable(self.act) + _trainable(self.cri)]
+            for opt, module in ((self.act_optimizer, self.act), (self.cri_optimizer, self.cri)):
+                for p in _trainable(module):
+                    tensors += [opt.state[p]["exp_avg"], opt.state[p]["exp_avg_sq"]]
+            flat = th.cat([t.reshape(-1) for t in tensors])
+            dist.broadcast(flat, src=dist.get_global_rank(self._dist_group, 0), group=self._dist_group)
+            th._foreach_copy_(tensors, [c.view_as(t) for c, t in zip(flat.split([t.numel() for t in tensors]), tensors)])
+            return
+        # ---- alternative: per-minibatch gradient all-reduce (b200rl_ppo_grads -> NCCL -> b200rl_ppo_apply)
         grad_numel = lib.b200rl_grad_numel(C.byref(act_desc), C.byref(cri_desc))
         grad_off = lib.b200rl_workspace_grad_offset()
         flat_grads = workspace[grad_off:grad_off + 4 * grad_numel].view(th.float32)

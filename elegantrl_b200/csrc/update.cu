@@ -213,28 +213,46 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
 // Gradient phase of one (sample tile, net): gather -> forward -> loss -> backward, RED.ADD into `grads` (flat buffer
 // of BOTH nets), loss sums into A.loss_sums.  WM: where the parameters are read from (mlp_tile.cuh); with W_SMEM the
 // net's parameters are first staged into shared memory with coalesced L2-coherent loads (small nets).
+#ifdef B200RL_PROFILE_PHASES
+#define PHASE_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) reinterpret_cast<long long*>(A.hdr)[8 + (i)] = clock64(); } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 template <int WM>
 DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, uint64_t draw, float* grads, float* smem,
                      int64_t* s_tn) {
     const int H = A.buf.horizon_len, N = A.buf.num_envs;
+    // packed mode (horizon_len == 0): `states` points at records {state[S], action[A], unmask, logprob, advantage
+    // (already normalised), reward_sum} written by b200rl_pack_minibatches (and all-gathered across ranks); id = record
+    const bool packed = (H == 0);
+    const int rec_act = A.net[0].dims[0], rec_tail = (A.net[0].dims[0] + A.net[0].dims[A.net[0].num_linear] + 3) & ~3;
+    const int rec = rec_tail + 4;
     const int slot0 = tile * UTB;
     float* sc = smem + A.smem_scalar_off;  // per-sample scalars
     float* s_unmask = sc, *s_logp = sc + UTB, *s_adv = sc + 2 * UTB, *s_rsum = sc + 3 * UTB, *s_act = sc + 4 * UTB;
 
+    PHASE_MARK(0);
     // ---- gather (reference :178-187): ids -> (t = id % H, n = id / H)
     if (threadIdx.x < UTB) {
         const int b = threadIdx.x, slot = slot0 + b;
         int64_t tn = -1;
         float um = 0.f, lp = 0.f, adv = 0.f, rs = 0.f;
         if (slot < A.local_batch) {
-            int64_t id = ids ? ids[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
-            int64_t t = id % H, n = id / H;
-            tn = t * N + n;
-            um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
-            lp = A.buf.logprobs[tn];
-            adv = A.buf.advantages[tn];
-            if (A.buf.adv_stats) adv = (adv - A.buf.adv_stats[0]) / (A.buf.adv_stats[1] + 1e-5f);
-            rs = A.buf.reward_sums[tn];
+            if (packed) {
+                tn = ids ? ids[slot] : (int64_t)draw * A.local_batch + slot;  // default: minibatch u = records [u*B, (u+1)*B)
+                const float4 tail = *reinterpret_cast<const float4*>(A.buf.states + tn * rec + rec_tail);
+                um = tail.x; lp = tail.y; adv = tail.z; rs = tail.w;
+            } else {
+                int64_t id = ids ? ids[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+                int64_t t = id % H, n = id / H;
+                tn = t * N + n;
+                um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
+                lp = A.buf.logprobs[tn];
+                adv = A.buf.advantages[tn];
+                if (A.buf.adv_stats) adv = (adv - A.buf.adv_stats[0]) / (A.buf.adv_stats[1] + 1e-5f);
+                rs = A.buf.reward_sums[tn];
+            }
         }
         s_tn[b] = tn; s_unmask[b] = um; s_logp[b] = lp; s_adv[b] = adv; s_rsum[b] = rs;
     }
@@ -243,12 +261,13 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
         const int Adim = A.net[0].dims[A.net[0].num_linear];
         for (int idx = threadIdx.x; idx < UTB * Adim; idx += kUpdThreads) {
             int b = idx / Adim, a = idx - b * Adim;
-            s_act[a * UTB + b] = s_tn[b] >= 0 ? A.buf.actions[s_tn[b] * Adim + a] : 0.0f;
+            s_act[a * UTB + b] = s_tn[b] < 0 ? 0.0f : (packed ? A.buf.states[s_tn[b] * rec + rec_act + a] : A.buf.actions[s_tn[b] * Adim + a]);
         }
     }
     const float inv_bsz = 1.0f / (float)A.global_batch;
     float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;  // valid in threads < UTB
 
+    PHASE_MARK(1);
     const b200rl_net& net = A.net[ni];
     const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
     const float* Wl[B200RL_MAX_LINEAR];
@@ -283,12 +302,13 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
         int b = idx / S, k = idx - b * S;
         float v = 0.0f;
         if (s_tn[b] >= 0) {
-            v = A.buf.states[s_tn[b] * S + k];
+            v = packed ? A.buf.states[s_tn[b] * rec + k] : A.buf.states[s_tn[b] * S + k];
             if (net.state_avg) v = (v - net.state_avg[k]) / (net.state_std[k] + 1e-4f);
         }
         smem[xoff[0] + UT::elem(k, b)] = v;
     }
     __syncthreads();
+    PHASE_MARK(2);
     // forward, keeping every layer input and act'
     for (int l = 0; l < L; ++l) {
         const bool hidden = l < L - 1;
@@ -296,6 +316,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
                                                    hidden ? smem + xoff[l + 1] : dzA, hidden ? smem + goff[l + 1] : nullptr,
                                                    net.activation, hidden);
         __syncthreads();
+        PHASE_MARK(3 + l);
     }
     // loss and d loss / d output, in place in dzA
     float* g = grads + A.grad_off[ni];
@@ -338,6 +359,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
         }
     }
     __syncthreads();
+    PHASE_MARK(6);
     // backward
     float* dz = dzA;
     float* dzn = dzB;
@@ -349,6 +371,7 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
         weight_grad(dz, smem + xoff[l], J, K, g + woff[l], g + woff[l] + J * K);
         if (l > 0) data_grad<WM>(Wl[l], dz, smem + goff[l], dzn, J, K);
         __syncthreads();
+        PHASE_MARK(7 + (L - 1 - l));
         float* t = dz; dz = dzn; dzn = t;
     }
 
@@ -415,13 +438,17 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_update_cluster_kernel(const _
         const int64_t* ids_u = A.ids ? A.ids + (size_t)u * A.local_batch : nullptr;
         if (A.stage_weights) grads_phase<W_SMEM>(A, tile, ni, ids_u, A.draw + (uint64_t)u, gcur, smem, s_tn);
         else grads_phase<W_LDCG>(A, tile, ni, ids_u, A.draw + (uint64_t)u, gcur, smem, s_tn);
+        PHASE_MARK(10);
         __threadfence();
         cluster.sync();
+        PHASE_MARK(11);
         // this net's CTAs share its clip + Adam; they also re-zero the other gradient buffer for minibatch u + 1
         apply_net(A.net[ni], A.opt[ni], s_adam, gcur + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red, tile, tiles);
+        PHASE_MARK(12);
         for (int i = blockIdx.x * kUpdThreads + threadIdx.x; i < gtotal; i += gridDim.x * kUpdThreads) gnext[i] = 0.0f;
         __threadfence();
         cluster.sync();
+        PHASE_MARK(13);
     }
     if (blockIdx.x == 0 && threadIdx.x < 3)
         A.out_scalars[threadIdx.x] = (float)(__ldcg(A.loss_sums + threadIdx.x) / (double)A.update_times);
@@ -431,6 +458,29 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_apply_kernel(const __grid_con
     __shared__ float red[32];
     const int ni = blockIdx.x;  // one CTA per net
     apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+}
+
+// One thread per sampled transition: draw / read its index, gather the six fields, normalise the advantage, and write a
+// 16-byte aligned record {state[S], action[A], pad to a multiple of 4, unmask, logprob, advantage, reward_sum}.
+__global__ void pack_minibatches_kernel(const b200rl_train_buffer buf, int S, int Adim, int local_batch, int update_times,
+                                        const int64_t* ids, uint64_t seed, uint64_t draw_offset, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= local_batch * update_times) return;
+    const int u = i / local_batch, slot = i - u * local_batch;
+    const int H = buf.horizon_len, N = buf.num_envs;
+    const int64_t id = ids ? ids[i] : sample_index(seed, draw_offset + (uint64_t)u, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+    const int64_t t = id % H, n = id / H, tn = t * N + n;
+    const int tail = (S + Adim + 3) & ~3;
+    float* r = out + (size_t)i * (tail + 4);
+    for (int k = 0; k < S; ++k) r[k] = buf.states[tn * S + k];
+    for (int a = 0; a < Adim; ++a) r[S + a] = buf.actions[tn * Adim + a];
+    for (int k = S + Adim; k < tail; ++k) r[k] = 0.0f;
+    float adv = buf.advantages[tn];
+    if (buf.adv_stats) adv = (adv - buf.adv_stats[0]) / (buf.adv_stats[1] + 1e-5f);
+    r[tail + 0] = buf.unmasks[tn] ? 1.0f : 0.0f;
+    r[tail + 1] = buf.logprobs[tn];
+    r[tail + 2] = adv;
+    r[tail + 3] = buf.reward_sums[tn];
 }
 
 __global__ void loss_means_kernel(const double* loss_sums, double inv_updates, float* out) {
@@ -501,8 +551,12 @@ int fill_args(UpdateArgs& A, const b200rl_net* actor, const b200rl_net* critic, 
 }
 
 int check_buffer(const b200rl_train_buffer* b) {
-    B200RL_REQUIRE(b && b->states && b->actions && b->unmasks && b->logprobs && b->advantages && b->reward_sums,
-                   "ppo: NULL training buffer field");
+    B200RL_REQUIRE(b && b->states, "ppo: NULL training buffer");
+    if (b->horizon_len == 0) {  // packed records (b200rl_pack_minibatches)
+        B200RL_REQUIRE(b->num_envs >= 1, "ppo: packed buffer with %d records", b->num_envs);
+        return 0;
+    }
+    B200RL_REQUIRE(b->actions && b->unmasks && b->logprobs && b->advantages && b->reward_sums, "ppo: NULL training buffer field");
     B200RL_REQUIRE(b->horizon_len >= 1 && b->num_envs >= 1, "ppo: horizon_len=%d num_envs=%d", b->horizon_len, b->num_envs);
     return 0;
 }
@@ -612,6 +666,20 @@ int b200rl_ppo_apply(const b200rl_net* actor, const b200rl_net* critic, b200rl_a
     B200RL_CHECK_CUDA(cudaGetLastError());
     actor_opt->step += 1;
     critic_opt->step += 1;
+    return 0;
+}
+
+int b200rl_pack_minibatches(const b200rl_train_buffer* buffer, int32_t state_dim, int32_t action_dim, int32_t local_batch,
+                            int32_t update_times, const int64_t* ids, uint64_t seed, uint64_t draw_offset, float* out_records,
+                            void* stream) {
+    if (int rc = check_buffer(buffer)) return rc;
+    B200RL_REQUIRE(buffer->horizon_len >= 1, "pack_minibatches: source buffer must not be packed itself");
+    B200RL_REQUIRE(out_records && local_batch >= 1 && update_times >= 1, "pack_minibatches: bad arguments");
+    const int total = local_batch * update_times;
+    pack_minibatches_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*buffer, state_dim, action_dim, local_batch,
+                                                                                  update_times, ids, seed, draw_offset, out_records);
+    B200RL_COUNT_LAUNCH(1);
+    B200RL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -173,7 +173,17 @@ B200RL_API int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* crit
                       uint64_t draw_offset, float* out_scalars, void* workspace, int64_t workspace_bytes,
                       void* stream);
 
-/* Multi-GPU split of one minibatch update.  b200rl_ppo_grads leaves this rank's gradient SUM over its
+/* Env-sharded (multi-GPU) update, preferred form: every rank packs ITS share of all the minibatches of one
+ * update_net -- update_times x local_batch sampled transitions -- into records of R = roundup4(state_dim + action_dim)
+ * + 4 floats {state, action, pad, unmask, logprob, normalised advantage, reward_sum}; the caller all-gathers them (ONE
+ * collective per cycle, ~30 KB) and then calls b200rl_ppo_update on every rank with a PACKED buffer:
+ * b200rl_train_buffer{states = records, horizon_len = 0, num_envs = number of records}, ids[u][i] = record index.
+ * ids: [update_times, local_batch] local indices into this rank's [H, N] buffer, or NULL (Philox). */
+B200RL_API int b200rl_pack_minibatches(const b200rl_train_buffer* buffer, int32_t state_dim, int32_t action_dim,
+                                       int32_t local_batch, int32_t update_times, const int64_t* ids, uint64_t seed,
+                                       uint64_t draw_offset, float* out_records, void* stream);
+
+/* Multi-GPU split of one minibatch update (gradient all-reduce form).  b200rl_ppo_grads leaves this rank's gradient SUM over its
  * `local_batch` samples, already divided by `global_batch`, in the workspace's flat buffer (zeroing it first)
  * and accumulates the three loss sums into loss_sums (device double[3], caller zeroes once per update_net);
  * the caller all-reduces (sum) the flat buffer; b200rl_ppo_apply does clip + Adam from it on every rank. */

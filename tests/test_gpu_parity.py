@@ -441,3 +441,44 @@ def test_checkpoint_roundtrip_and_actor_pickle(tmp_path):
     before = other.act.net[0].weight.clone()
     other.update_net(buffer)
     assert not th.equal(before, other.act.net[0].weight)
+
+
+@pytest.mark.parametrize("case", gu.SYNTH_CASES)
+def test_packed_minibatches_equal_direct_gather(case, update_impl):
+    """The env-sharded path packs the sampled transitions into records (b200rl_pack_minibatches), all-gathers them and
+    runs the update on the packed buffer: on one rank that must reproduce the reference exactly like the direct path."""
+    g = gu.load(case)
+    agent = G.agent_from_golden(g)
+    lib = _lib.load()
+    ids = G.cuda(g["update.ids"])
+    updates, batch = ids.shape
+    keys = ("buf.states", "buf.actions", "buf.unmasks", "buf.logprobs", "gae.advantages", "gae.reward_sums")
+    states, actions, unmasks, logprobs, advantages, reward_sums = [G.cuda(g[k]) for k in keys]
+    stats = G.cuda(np.array([g["gae.adv_mean"], g["gae.adv_std"], 0, 0], dtype=np.float32))
+    h, n = states.shape[:2]
+    tb = _lib.TrainBuffer(states=states.data_ptr(), actions=actions.data_ptr(), unmasks=unmasks.data_ptr(),
+                          logprobs=logprobs.data_ptr(), advantages=advantages.data_ptr(), reward_sums=reward_sums.data_ptr(),
+                          adv_stats=stats.data_ptr(), horizon_len=h, num_envs=n)
+    rec = ((agent.state_dim + agent.action_dim + 3) & ~3) + 4
+    records = th.full((updates * batch, rec), float("nan"), device="cuda:0")
+    _lib.check(lib.b200rl_pack_minibatches(C.byref(tb), agent.state_dim, agent.action_dim, batch, updates, ids.data_ptr(), 0, 0,
+                                           records.data_ptr(), None))
+    rec_np = records.cpu().numpy()
+    ids0, ids1 = po.split_ids(g["update.ids"].reshape(-1), h)
+    np.testing.assert_array_equal(rec_np[:, :agent.state_dim], g["buf.states"][ids0, ids1])       # gathers: bit-exact
+    np.testing.assert_array_equal(rec_np[:, rec - 4], g["buf.unmasks"][ids0, ids1].astype(np.float32))
+    np.testing.assert_allclose(rec_np[:, rec - 2], g["gae.adv_norm"][ids0, ids1], rtol=1e-5, atol=1e-6)
+
+    act_desc, cri_desc = agent._net_desc(agent.act), agent._net_desc(agent.cri)
+    act_adam, cri_adam = agent._adam_desc(agent.act_optimizer, agent.act), agent._adam_desc(agent.cri_optimizer, agent.cri)
+    ws = agent._get_workspace(act_desc, cri_desc)
+    packed = _lib.TrainBuffer(states=records.data_ptr(), horizon_len=0, num_envs=records.shape[0])
+    hp = _lib.PPOHyper(ratio_clip=agent.ratio_clip, lambda_entropy=agent.lambda_entropy, clip_grad_norm=agent.clip_grad_norm)
+    out = th.empty(3, device="cuda:0")
+    _lib.check(lib.b200rl_ppo_update(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam), C.byref(packed),
+                                     C.byref(hp), batch, updates, None, 0, 0, out.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    G.assert_close(out, g["update.scalars"].mean(axis=0), RTOL, 1e-6)
+    for which, module in (("actor", agent.act), ("critic", agent.cri)):
+        got, ref = gu.flat_params(G.module_to_net(module)), gu.flat_params(gu.net_of(g, f"update.after.{which}"))
+        for a, b in zip(got, ref):
+            G.assert_close(a, b, RTOL, 2e-6, which)

@@ -35,8 +35,16 @@ def main():
     global_ids = np.concatenate([(env_l[r] + r * shard) * h + t_l[r] for r in range(world)], axis=1)  # [updates, batch]
 
     keys = ("states", "actions", "logprobs", "rewards", "undones", "unmasks")
+    for mode in ("gather", "allreduce"):
+        run_mode(mode, g, rank, world, local, dev, h, n, shard, lo, batch, updates, local_ids, global_ids, keys)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_mode(mode, g, rank, world, local, dev, h, n, shard, lo, batch, updates, local_ids, global_ids, keys):
     agent = G.agent_from_golden(g, gpu_id=local, batch_size=batch, repeat_times=updates * batch / h + 1e-9, num_envs=shard)
     agent.enable_data_parallel()
+    agent.sharded_mode = mode
     buf = [G.cuda(np.ascontiguousarray(g[f"buf.{k}"][:, lo:lo + shard]), dev) for k in keys]
     agent.last_state = G.cuda(g["buf.last_state"][lo:lo + shard], dev)
     agent._inject_ids = G.cuda(local_ids[rank], dev)
@@ -58,9 +66,7 @@ def main():
         np.testing.assert_allclose(flat.cpu().numpy(), sflat.cpu().numpy(), rtol=1e-4, atol=2e-6)
         np.testing.assert_allclose(agent.last_update_info["adv_stats"][:2].cpu().numpy(),
                                    single.last_update_info["adv_stats"][:2].cpu().numpy(), rtol=1e-5)
-        print(f"| multi-GPU check ok on {world} ranks: sharded == single-GPU, result {tuple(round(x, 6) for x in res)}")
-    dist.barrier()
-    dist.destroy_process_group()
+        print(f"| multi-GPU check ok on {world} ranks [{mode}]: sharded == single-GPU, result {tuple(round(x, 6) for x in res)}")
 
 
 if __name__ == "__main__":
