@@ -214,7 +214,8 @@ def run_engine(args):
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.b200rl_launch_count() - launches0
-    rollout_ms = statistics.mean(a.elapsed_time(b) for a, b in roll_events)
+    rollout_list = [a.elapsed_time(b) for a, b in roll_events]
+    rollout_ms = statistics.median(rollout_list)  # median: robust against a straggler launch
     assert th.isfinite(out).all(), "non-finite losses"
     t = th.tensor([elapsed_ms], dtype=th.float64, device=dev)
     if world > 1:
@@ -245,6 +246,7 @@ def run_engine(args):
     roofline = {"kernel": "rollout_pendulum_tc_kernel (fused env + actor + critic + trajectory stores; 64x64 layers on tcgen05, 3xTF32)", "bound": "tensor",
                 "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
                 "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": rollout_ms,
+                "launch_ms_min_max": [min(rollout_list), max(rollout_list)],
                 "share_of_step": rollout_ms / (elapsed_ms / args.steps),
                 "pipe": "algorithmic MLP FLOPs (17 408 per env-step, fp32-equivalent) over the measured bf16 tensor peak; the kernel itself is bound by the CUDA-core side (256 GELUs per env-step), see DESIGN.md",
                 "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
