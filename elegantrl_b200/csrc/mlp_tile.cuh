@@ -74,35 +74,47 @@ template <int WM>
 DEV float ld_param(const float* p) { return WM == W_LDG ? __ldg(p) : (WM == W_LDCG ? __ldcg(p) : *p); }
 
 // copy W [J][K] (global, coherent loads) into the shared-memory layout WeightView<W_SMEM> reads
-template <int NT>
-DEV void stage_weight(const float* __restrict__ W, int J, int K, float* dst) {
+// (executed by the `nthreads` threads tid = 0 .. nthreads-1 of the caller's choice)
+DEV void stage_weight(const float* __restrict__ W, int J, int K, float* dst, int tid, int nthreads) {
     const bool swz = (K & 31) == 0;
     if (((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0)) {
         const int chunks = K >> 2;
-        for (int i = threadIdx.x; i < J * chunks; i += NT) {
+        for (int i = tid; i < J * chunks; i += nthreads) {
             const int j = i / chunks, c = i - j * chunks;
             const float4 v = __ldcg(reinterpret_cast<const float4*>(W) + i);
             const int cs = swz ? ((c & ~7) | ((c ^ (j >> 2)) & 7)) : c;
             *reinterpret_cast<float4*>(dst + j * K + (cs << 2)) = v;
         }
     } else {
-        for (int i = threadIdx.x; i < J * K; i += NT) dst[i] = __ldcg(W + i);
+        for (int i = tid; i < J * K; i += nthreads) dst[i] = __ldcg(W + i);
+    }
+}
+
+// activation and its derivative from ONE erf evaluation (GELU) -- used by the update's forward pass
+DEV void act_and_grad(float z, int act, float& h, float& g) {
+    if (act == B200RL_ACT_GELU) {
+        const float cdf = 0.5f * (1.0f + erff(z * kSqrtHalf));
+        h = z * cdf;  // == z * 0.5 * (1 + erf(z / sqrt 2)) up to one rounding
+        g = cdf + z * (expf(-0.5f * z * z) * kInvSqrt2Pi);
+    } else {
+        h = fmaxf(z, 0.0f);
+        g = z > 0.0f ? 1.0f : 0.0f;
     }
 }
 
 // Ys[j][b] = act(sum_k W[j][k] * Xs[k][b] + bias[j]); optionally Gs[j][b] = act'(pre-activation).
-// Thread tile: 4 samples x 4 outputs.
-template <int TB, int NT, int WM = W_LDG>
-DEV void linear_forward(const float* Wp, const float* bias, int K, int J, const float* Xs, float* Ys, float* Gs, int act,
-                        bool apply_act) {
+// Thread tile: 4 samples x JT outputs (JT = 4, or 2 for narrow layers so that every thread of the CTA has work).
+template <int TB, int NT, int WM, int JT>
+DEV void linear_forward_tile(const float* Wp, const float* bias, int K, int J, const float* Xs, float* Ys, float* Gs, int act,
+                             bool apply_act) {
     constexpr int NSG = TB / 4, NOL = NT / NSG;
     using T = SmemTile<TB>;
     const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
     const WeightView<WM> W(Wp, K);
-    for (int j0 = ol * 4; j0 < J; j0 += NOL * 4) {
-        float acc[4][4];
+    for (int j0 = ol * JT; j0 < J; j0 += NOL * JT) {
+        float acc[JT][4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < JT; ++jj) {
             float bv = (j0 + jj < J) ? ld_param<WM>(bias + j0 + jj) : 0.0f;
 #pragma unroll
             for (int s = 0; s < 4; ++s) acc[jj][s] = bv;
@@ -114,7 +126,7 @@ DEV void linear_forward(const float* Wp, const float* bias, int K, int J, const 
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) xv[kk] = ld4(Xs + T::chunk(k + kk, sg));
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < JT; ++jj) {
                     if (j0 + jj < J) {
                         float4 w = W.ld4(j0 + jj, k);
                         acc[jj][0] = fmaf(w.x, xv[0].x, acc[jj][0]); acc[jj][1] = fmaf(w.x, xv[0].y, acc[jj][1]);
@@ -132,7 +144,7 @@ DEV void linear_forward(const float* Wp, const float* bias, int K, int J, const 
             for (int k = 0; k < K; ++k) {
                 float4 xv = ld4(Xs + T::chunk(k, sg));
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < JT; ++jj) {
                     if (j0 + jj < J) {
                         float w = W.ld1(j0 + jj, k);
                         acc[jj][0] = fmaf(w, xv.x, acc[jj][0]); acc[jj][1] = fmaf(w, xv.y, acc[jj][1]);
@@ -142,18 +154,29 @@ DEV void linear_forward(const float* Wp, const float* bias, int K, int J, const 
             }
         }
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < JT; ++jj) {
             if (j0 + jj < J) {
                 float4 y = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
                 if (apply_act) {
                     if (Gs) {
-                        st4(Gs + T::chunk(j0 + jj, sg), make_float4(act_grad_rt(y.x, act), act_grad_rt(y.y, act),
-                                                                    act_grad_rt(y.z, act), act_grad_rt(y.w, act)));
+                        float4 g;
+                        act_and_grad(y.x, act, y.x, g.x); act_and_grad(y.y, act, y.y, g.y);
+                        act_and_grad(y.z, act, y.z, g.z); act_and_grad(y.w, act, y.w, g.w);
+                        st4(Gs + T::chunk(j0 + jj, sg), g);
+                    } else {
+                        y = make_float4(act_fn_rt(y.x, act), act_fn_rt(y.y, act), act_fn_rt(y.z, act), act_fn_rt(y.w, act));
                     }
-                    y = make_float4(act_fn_rt(y.x, act), act_fn_rt(y.y, act), act_fn_rt(y.z, act), act_fn_rt(y.w, act));
                 }
                 st4(Ys + T::chunk(j0 + jj, sg), y);
             }
         }
     }
+}
+
+template <int TB, int NT, int WM = W_LDG>
+DEV void linear_forward(const float* Wp, const float* bias, int K, int J, const float* Xs, float* Ys, float* Gs, int act,
+                        bool apply_act) {
+    constexpr int NOL = NT / (TB / 4);
+    if (J <= NOL * 2) linear_forward_tile<TB, NT, WM, 2>(Wp, bias, K, J, Xs, Ys, Gs, act, apply_act);
+    else linear_forward_tile<TB, NT, WM, 4>(Wp, bias, K, J, Xs, Ys, Gs, act, apply_act);
 }

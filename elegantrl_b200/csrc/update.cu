@@ -98,38 +98,41 @@ DEV void weight_grad(const float* dZ, const float* X, int J, int K, float* gW, f
     }
 }
 
-// dZprev[k][b] = (sum_j W[j][k] * dZ[j][b]) * G[k][b]
-template <int WM>
-DEV void data_grad(const float* Wp, const float* dZ, const float* G, float* dZprev, int J, int K) {
+// dZprev[k][b] = (sum_j W[j][k] * dZ[j][b]) * G[k][b]     thread tile: 4 samples x KT inputs (KT = 4, or 2 when K is
+// small enough that 4-wide tiles would leave half of the CTA idle)
+template <int WM, int KT>
+DEV void data_grad_tile(const float* Wp, const float* dZ, const float* G, float* dZprev, int J, int K) {
     constexpr int NSG = UTB / 4, NOL = kUpdThreads / NSG;
     const int sg = threadIdx.x % NSG, ol = threadIdx.x / NSG;
     const WeightView<WM> W(Wp, K);
     const bool vec = W.vec;
-    for (int k0 = ol * 4; k0 < K; k0 += NOL * 4) {
-        float acc[4][4];
+    for (int k0 = ol * KT; k0 < K; k0 += NOL * KT) {
+        float acc[KT][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < KT; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
 #pragma unroll 4
         for (int j = 0; j < J; ++j) {
             float4 dz = ld4(dZ + UT::chunk(j, sg));
-            float w[4];
+            float w[KT];
             if (vec) {
-                float4 w4 = W.ld4(j, k0);
-                w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+                float4 w4 = W.ld4(j, k0 & ~3);
+                if (KT == 4) { w[0] = w4.x; w[1] = w4.y; w[KT - 2] = w4.z; w[KT - 1] = w4.w; }
+                else if (k0 & 2) { w[0] = w4.z; w[1] = w4.w; }
+                else { w[0] = w4.x; w[1] = w4.y; }
             } else {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) w[kk] = (k0 + kk < K) ? W.ld1(j, k0 + kk) : 0.0f;
+                for (int kk = 0; kk < KT; ++kk) w[kk] = (k0 + kk < K) ? W.ld1(j, k0 + kk) : 0.0f;
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < KT; ++kk) {
                 acc[kk][0] = fmaf(w[kk], dz.x, acc[kk][0]); acc[kk][1] = fmaf(w[kk], dz.y, acc[kk][1]);
                 acc[kk][2] = fmaf(w[kk], dz.z, acc[kk][2]); acc[kk][3] = fmaf(w[kk], dz.w, acc[kk][3]);
             }
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < KT; ++kk) {
             if (k0 + kk < K) {
                 float4 g = ld4(G + UT::chunk(k0 + kk, sg));
                 st4(dZprev + UT::chunk(k0 + kk, sg),
@@ -137,6 +140,12 @@ DEV void data_grad(const float* Wp, const float* dZ, const float* G, float* dZpr
             }
         }
     }
+}
+template <int WM>
+DEV void data_grad(const float* Wp, const float* dZ, const float* G, float* dZprev, int J, int K) {
+    constexpr int NOL = kUpdThreads / (UTB / 4);
+    if (K <= NOL * 2) data_grad_tile<WM, 2>(Wp, dZ, G, dZprev, J, K);
+    else data_grad_tile<WM, 4>(Wp, dZ, G, dZprev, J, K);
 }
 
 DEV float block_sum(float v, float* red /*[32]*/) {
@@ -171,42 +180,82 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
     float coef = 1.0f;
     if (clip_grad_norm > 0.0f) coef = fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f);
     const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps;
-    int off = 0;
     const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
     const int first = part * kUpdThreads + threadIdx.x, stride = nparts * kUpdThreads;
-    for (int ti = 0; ti < n_tensors; ++ti) {
-        float *p, *m, *v;
-        int count;
-        const int l = ti >> 1;
-        if (ti == 2 * net.num_linear) {
-            p = net.action_std_log; m = opt.exp_avg_std; v = opt.exp_avg_sq_std; count = net.dims[net.num_linear];
-        } else if ((ti & 1) == 0) {
-            p = net.weight[l]; m = opt.exp_avg_w[l]; v = opt.exp_avg_sq_w[l]; count = net.dims[l + 1] * net.dims[l];
-        } else {
-            p = net.bias[l]; m = opt.exp_avg_b[l]; v = opt.exp_avg_sq_b[l]; count = net.dims[l + 1];
-        }
-        const bool vec = ((count & 3) == 0) &&
-                         (((reinterpret_cast<uintptr_t>(g + off) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) |
-                            reinterpret_cast<uintptr_t>(v)) & 15) == 0);
-        if (vec) {  // 128-bit path: four independent parameter lanes per thread and iteration
-            const float4* g4 = reinterpret_cast<const float4*>(g + off);
-            float4 *p4 = reinterpret_cast<float4*>(p), *m4 = reinterpret_cast<float4*>(m), *v4 = reinterpret_cast<float4*>(v);
-            for (int i = first; i < (count >> 2); i += stride) {
-                float4 gg = __ldcg(g4 + i), pp = __ldcg(p4 + i), mm = __ldcg(m4 + i), vv = __ldcg(v4 + i);
-                adam_one(pp.x, mm.x, vv.x, gg.x * coef, b1, b2, eps, as);
-                adam_one(pp.y, mm.y, vv.y, gg.y * coef, b1, b2, eps, as);
-                adam_one(pp.z, mm.z, vv.z, gg.z * coef, b1, b2, eps, as);
-                adam_one(pp.w, mm.w, vv.w, gg.w * coef, b1, b2, eps, as);
-                p4[i] = pp; m4[i] = mm; v4[i] = vv;
-            }
-        } else {
-            for (int i = first; i < count; i += stride) {
-                float pi = __ldcg(p + i), mi = __ldcg(m + i), vi = __ldcg(v + i);
-                adam_one(pi, mi, vi, __ldcg(g + off + i) * coef, b1, b2, eps, as);
-                p[i] = pi; m[i] = mi; v[i] = vi;
+    // Every tensor is visited in rounds of up to kBatch tensors: all loads of a round are issued before any
+    // arithmetic / store, so their (L2) latencies overlap instead of adding up tensor after tensor.
+    constexpr int kBatch = 4;
+    int off = 0;
+    for (int t0 = 0; t0 < n_tensors; t0 += kBatch) {
+        float* P[kBatch]; float* M[kBatch]; float* V[kBatch];
+        int cnt[kBatch], goff[kBatch];
+        bool vecs[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const int ti = t0 + q;
+            cnt[q] = 0; goff[q] = off; vecs[q] = false; P[q] = M[q] = V[q] = nullptr;
+            if (ti < n_tensors) {
+                const int l = ti >> 1;
+                if (ti == 2 * net.num_linear) {
+                    P[q] = net.action_std_log; M[q] = opt.exp_avg_std; V[q] = opt.exp_avg_sq_std; cnt[q] = net.dims[net.num_linear];
+                } else if ((ti & 1) == 0) {
+                    P[q] = net.weight[l]; M[q] = opt.exp_avg_w[l]; V[q] = opt.exp_avg_sq_w[l]; cnt[q] = net.dims[l + 1] * net.dims[l];
+                } else {
+                    P[q] = net.bias[l]; M[q] = opt.exp_avg_b[l]; V[q] = opt.exp_avg_sq_b[l]; cnt[q] = net.dims[l + 1];
+                }
+                vecs[q] = ((cnt[q] & 3) == 0) &&
+                          (((reinterpret_cast<uintptr_t>(g + off) | reinterpret_cast<uintptr_t>(P[q]) | reinterpret_cast<uintptr_t>(M[q]) |
+                             reinterpret_cast<uintptr_t>(V[q])) & 15) == 0);
+                off += cnt[q];
             }
         }
-        off += count;
+        // first item of every tensor of the round (covers whole tensors up to 4 * stride floats): batched loads
+        float4 gg[kBatch], pp[kBatch], mm[kBatch], vv[kBatch];
+        bool have[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            have[q] = vecs[q] && first < (cnt[q] >> 2);
+            if (have[q]) {
+                gg[q] = __ldcg(reinterpret_cast<const float4*>(g + goff[q]) + first);
+                pp[q] = __ldcg(reinterpret_cast<const float4*>(P[q]) + first);
+                mm[q] = __ldcg(reinterpret_cast<const float4*>(M[q]) + first);
+                vv[q] = __ldcg(reinterpret_cast<const float4*>(V[q]) + first);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            if (have[q]) {
+                adam_one(pp[q].x, mm[q].x, vv[q].x, gg[q].x * coef, b1, b2, eps, as);
+                adam_one(pp[q].y, mm[q].y, vv[q].y, gg[q].y * coef, b1, b2, eps, as);
+                adam_one(pp[q].z, mm[q].z, vv[q].z, gg[q].z * coef, b1, b2, eps, as);
+                adam_one(pp[q].w, mm[q].w, vv[q].w, gg[q].w * coef, b1, b2, eps, as);
+                reinterpret_cast<float4*>(P[q])[first] = pp[q];
+                reinterpret_cast<float4*>(M[q])[first] = mm[q];
+                reinterpret_cast<float4*>(V[q])[first] = vv[q];
+            }
+        }
+        // remaining items (large tensors) and tensors that cannot be accessed as float4
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            if (vecs[q]) {
+                const float4* g4 = reinterpret_cast<const float4*>(g + goff[q]);
+                float4 *p4 = reinterpret_cast<float4*>(P[q]), *m4 = reinterpret_cast<float4*>(M[q]), *v4 = reinterpret_cast<float4*>(V[q]);
+                for (int i = first + stride; i < (cnt[q] >> 2); i += stride) {
+                    float4 a = __ldcg(g4 + i), b = __ldcg(p4 + i), c = __ldcg(m4 + i), d = __ldcg(v4 + i);
+                    adam_one(b.x, c.x, d.x, a.x * coef, b1, b2, eps, as);
+                    adam_one(b.y, c.y, d.y, a.y * coef, b1, b2, eps, as);
+                    adam_one(b.z, c.z, d.z, a.z * coef, b1, b2, eps, as);
+                    adam_one(b.w, c.w, d.w, a.w * coef, b1, b2, eps, as);
+                    p4[i] = b; m4[i] = c; v4[i] = d;
+                }
+            } else {
+                for (int i = first; i < cnt[q]; i += stride) {
+                    float pi = __ldcg(P[q] + i), mi = __ldcg(M[q] + i), vi = __ldcg(V[q] + i);
+                    adam_one(pi, mi, vi, __ldcg(g + goff[q] + i) * coef, b1, b2, eps, as);
+                    P[q][i] = pi; M[q][i] = mi; V[q][i] = vi;
+                }
+            }
+        }
     }
 }
 
@@ -232,6 +281,31 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
     float* sc = smem + A.smem_scalar_off;  // per-sample scalars
     float* s_unmask = sc, *s_logp = sc + UTB, *s_adv = sc + 2 * UTB, *s_rsum = sc + 3 * UTB, *s_act = sc + 4 * UTB;
 
+    // ---- parameters first: their staging loads overlap the dependent load chain of the index gather below
+    const b200rl_net& net = A.net[ni];
+    const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
+    const float* Wl[B200RL_MAX_LINEAR];
+    const float* bl[B200RL_MAX_LINEAR];
+    const float* std_log = net.action_std_log;
+    if (WM == W_SMEM) {
+        // warps 1..7 stage; warp 0 goes straight to the index gather (a warp issues in order: it would otherwise sit
+        // on its own staging loads before starting the gather's dependent chain)
+        float* w = smem + A.smem_weight_off;
+        const int stid = (int)threadIdx.x - 32, snt = kUpdThreads - 32;
+        for (int l = 0; l < L; ++l) {
+            const int J = net.dims[l + 1], K = net.dims[l];
+            if (stid >= 0) stage_weight(net.weight[l], J, K, w, stid, snt);
+            Wl[l] = w; w += (J * K + 3) & ~3;
+            if (stid >= 0) for (int i = stid; i < J; i += snt) w[i] = __ldcg(net.bias[l] + i);
+            bl[l] = w; w += (J + 3) & ~3;
+        }
+        if (net.action_std_log) {
+            if (stid >= 0) for (int i = stid; i < OUT; i += snt) w[i] = __ldcg(net.action_std_log + i);
+            std_log = w;
+        }
+    } else {
+        for (int l = 0; l < L; ++l) { Wl[l] = net.weight[l]; bl[l] = net.bias[l]; }
+    }
     PHASE_MARK(0);
     // ---- gather (reference :178-187): ids -> (t = id % H, n = id / H)
     if (threadIdx.x < UTB) {
@@ -268,27 +342,6 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
     float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;  // valid in threads < UTB
 
     PHASE_MARK(1);
-    const b200rl_net& net = A.net[ni];
-    const int L = net.num_linear, S = net.dims[0], OUT = net.dims[L];
-    const float* Wl[B200RL_MAX_LINEAR];
-    const float* bl[B200RL_MAX_LINEAR];
-    const float* std_log = net.action_std_log;
-    if (WM == W_SMEM) {
-        float* w = smem + A.smem_weight_off;
-        for (int l = 0; l < L; ++l) {
-            const int J = net.dims[l + 1], K = net.dims[l];
-            stage_weight<kUpdThreads>(net.weight[l], J, K, w);
-            Wl[l] = w; w += (J * K + 3) & ~3;
-            for (int i = threadIdx.x; i < J; i += kUpdThreads) w[i] = __ldcg(net.bias[l] + i);
-            bl[l] = w; w += (J + 3) & ~3;
-        }
-        if (net.action_std_log) {
-            for (int i = threadIdx.x; i < OUT; i += kUpdThreads) w[i] = __ldcg(net.action_std_log + i);
-            std_log = w;
-        }
-    } else {
-        for (int l = 0; l < L; ++l) { Wl[l] = net.weight[l]; bl[l] = net.bias[l]; }
-    }
     // smem map: X[0..L-1] (inputs of each Linear), G[1..L-1] (act' at each hidden layer), dzA, dzB
     int xoff[B200RL_MAX_LINEAR + 1], goff[B200RL_MAX_LINEAR + 1];
     int off = 0;
