@@ -25,14 +25,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or this many ns pass)
+// instead of spinning through try_wait / YIELD / BRA and stealing issue slots from the warps that do the work
+constexpr uint32_t kSuspendHintNs = 20000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
