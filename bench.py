@@ -50,51 +50,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled every 25 ms DURING the timed region, in-process through NVML
+    (nvidia_ml_py).  An external `nvidia-smi -lms` loop was measured to stall kernel submission for up to 100 ms per
+    query on these hosts, which is as long as the whole timed region; the NVML calls below take microseconds."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.gpu_index, self.proc = gpu_index, None
+        import threading
+        self.samples, self.stop_flag, self.thread, self.handle, self.nv = [], threading.Event(), None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+            except Exception:
+                pass
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as err:  # noqa: BLE001
+            self.error = repr(err)
+
+    def _loop(self):
+        nv, h = self.nv, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except AttributeError:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, reasons))
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.025)
 
     def start(self):
-        """Start sampling and block until nvidia-smi has delivered its first sample: its start-up (NVML init)
-        perturbs kernel submission for ~100 ms and must not overlap the timed region."""
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.first_line = self.proc.stdout.readline()
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            return
+        import threading
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.first_timed = len(self.samples)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        out = getattr(self, "first_line", "") + out
-        sm, sm_max, reasons, power = [], [], set(), []
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); sm_max.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(sm_max), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "error", "?")]}
+        self.stop_flag.set()
+        self.thread.join()
+        timed = self.samples[getattr(self, "first_timed", 0):] or self.samples
+        if not timed:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+        reasons = sorted({name for _, _, r in timed for name, bit in self.REASONS if r & bit})
+        return {"sm_mhz": statistics.median(c for c, _, _ in timed), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(timed), "power_w_max": max(p for _, p, _ in timed), "how": "NVML in-process, 25 ms period"}
 
 
 def run_reference(args):
@@ -193,14 +206,15 @@ def run_engine(args):
     # ---- timed region 1: `value` -- inputs resident in HBM, no host round trips inside
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()          # returns after the first sample: nvidia-smi start-up is outside the timed region
-    for _ in range(150):         # ~0.4 s of the same load while the sampler collects (a fixed count: every rank
-        cycle_device()           # must issue the same number of collectives)
+        sampler.start()
+    for _ in range(20):          # a fixed count: every rank must issue the same number of collectives
+        cycle_device()
     th.cuda.synchronize()
     launches0 = lib.b200rl_launch_count()
     ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     roll_events = []
     barrier()
+    sampler.mark()
     ev0.record()
     for _ in range(args.steps):
         a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)

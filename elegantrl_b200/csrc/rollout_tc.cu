@@ -283,8 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
             const size_t rowbase = (size_t)t * N;
             float x[3] = {cos_t, sin_t, theta_dot};
             if (has_norm) { x[0] = (x[0] - avg0) / std0; x[1] = (x[1] - avg1) / std1; x[2] = (x[2] - avg2) / std2; }
-            const float mu = eval_net(ctx, x, lane);
-
+            // noise first: it does not depend on the policy output, so it is off the critical path to the next observation
             float e = 0.0f;
             float2 reset_u = make_float2(0.0f, 0.0f);
             if (P.eps == nullptr || P.reset_noise == nullptr) {
@@ -294,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
             }
             if (P.eps && live) e = P.eps[rowbase + n];
             if (P.reset_noise && live) reset_u = make_float2(P.reset_noise[(rowbase + n) * 2], P.reset_noise[(rowbase + n) * 2 + 1]);
+            const float mu = eval_net(ctx, x, lane);
             const float action = __fadd_rn(__fmul_rn(e, sd), mu);
             const float diff = __fsub_rn(action, mu);
             const float logprob = __fsub_rn(__fsub_rn(-__fdiv_rn(__fmul_rn(diff, diff), var2), log_sd), kLogSqrt2Pi);
