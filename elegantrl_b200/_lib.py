@@ -33,7 +33,11 @@ class Adam(C.Structure):
 
 class PPOHyper(C.Structure):
     _fields_ = [("ratio_clip", C.c_float), ("lambda_entropy", C.c_float), ("clip_grad_norm", C.c_float),
-                ("reserved", C.c_int32)]
+                ("flags", C.c_int32)]
+
+
+PPO_SMOOTH_L1, PPO_MIN_CLIP, PPO_ENTROPY_BONUS, PPO_ACTOR_UNMASKED, PPO_CRITIC_MASK_MEAN = 1, 2, 4, 8, 16
+PPO_HELLOWORLD = PPO_SMOOTH_L1 | PPO_MIN_CLIP | PPO_ENTROPY_BONUS | PPO_ACTOR_UNMASKED | PPO_CRITIC_MASK_MEAN
 
 
 class TrainBuffer(C.Structure):

@@ -77,8 +77,9 @@ class AgentPPO:
 
         # ---- fields of AgentPPO.__init__ (reference AgentPPO.py:18-32)
         activation = getattr(args, "activation", "gelu")
-        self.act = ActorPPO(self.net_dims, self.state_dim, self.action_dim, activation).to(self.device)
-        self.cri = CriticPPO(self.net_dims, self.state_dim, self.action_dim, activation).to(self.device)
+        state_norm = getattr(args, "use_state_norm", True)
+        self.act = ActorPPO(self.net_dims, self.state_dim, self.action_dim, activation, state_norm).to(self.device)
+        self.cri = CriticPPO(self.net_dims, self.state_dim, self.action_dim, activation, state_norm).to(self.device)
         self.act_target = self.cri_target = None
         self.act_optimizer = th.optim.Adam(self.act.parameters(), self.learning_rate)
         self.cri_optimizer = th.optim.Adam(self.cri.parameters(), self.learning_rate)
@@ -98,6 +99,8 @@ class AgentPPO:
         self._dist_group = None      # set by enable_data_parallel()
         self._rank, self._world = 0, 1
         self.last_update_info = {}
+        self._ppo_flags = 0          # b200rl_ppo_hyper.flags: 0 = the reference's elegantrl arithmetic
+        self._full_std = False       # advantage std over the whole buffer instead of the [::4, ::4] lattice
 
     # ------------------------------------------------------------------------------------ plumbing
     def _require_engine(self):
@@ -123,7 +126,7 @@ class AgentPPO:
             net.dims[i + 1] = layer.out_features
             net.weight[i] = self._check(layer.weight.data, "weight").data_ptr()
             net.bias[i] = self._check(layer.bias.data, "bias").data_ptr()
-        if hasattr(module, "state_avg"):
+        if getattr(module, "state_avg", None) is not None:
             net.state_avg = self._check(module.state_avg.data, "state_avg").data_ptr()
             net.state_std = self._check(module.state_std.data, "state_std").data_ptr()
         if hasattr(module, "action_std_log"):
@@ -356,8 +359,9 @@ class AgentPPO:
             import torch.distributed as dist
             dist.all_reduce(stat_sums, group=self._dist_group)
         stats = th.empty(4, dtype=th.float32, device=dev)
-        _lib.check(lib.b200rl_adv_stats(_lib.ptr(stat_sums), h * n_global, ((h + 3) // 4) * ((n_global + 3) // 4),
-                                        _lib.ptr(stats), self._stream()), "adv_stats")
+        count_lattice = 0 if self._full_std else ((h + 3) // 4) * ((n_global + 3) // 4)
+        _lib.check(lib.b200rl_adv_stats(_lib.ptr(stat_sums), h * n_global, count_lattice, _lib.ptr(stats), self._stream()),
+                   "adv_stats")
 
         update_times = int(h * self.repeat_times / self.batch_size)
         assert update_times >= 1
@@ -368,7 +372,7 @@ class AgentPPO:
                               logprobs=_lib.ptr(self._check(logprobs, "logprobs")), advantages=_lib.ptr(advantages),
                               reward_sums=_lib.ptr(reward_sums), adv_stats=_lib.ptr(stats), horizon_len=h, num_envs=n)
         hp = _lib.PPOHyper(ratio_clip=float(self.ratio_clip), lambda_entropy=float(self.lambda_entropy),
-                           clip_grad_norm=float(self.clip_grad_norm or 0.0))
+                           clip_grad_norm=float(self.clip_grad_norm or 0.0), flags=int(self._ppo_flags))
         out = th.empty(3, dtype=th.float32, device=dev)
         ids = getattr(self, "_inject_ids", None)
         if self._world == 1:

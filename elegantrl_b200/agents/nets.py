@@ -38,19 +38,24 @@ class _StateNormMixin:
     state_std: nn.Parameter
 
     def state_norm(self, state: TEN) -> TEN:
+        if self.state_avg is None:  # helloworld nets have no input normalisation
+            return state
         return (state - self.state_avg) / (self.state_std + 1e-4)
 
 
 class ActorPPO(nn.Module, _StateNormMixin):
     """Gaussian policy: mean = MLP(state_norm(s)), std = exp(action_std_log) (state independent)."""
 
-    def __init__(self, net_dims, state_dim: int, action_dim: int, activation: str = "gelu"):
+    def __init__(self, net_dims, state_dim: int, action_dim: int, activation: str = "gelu", state_norm: bool = True):
         super().__init__()
         self.net = make_mlp([state_dim, *net_dims, action_dim], activation)
-        _init_output_layer(self.net[-1], std=0.1)
         self.action_std_log = nn.Parameter(th.zeros((1, action_dim)), requires_grad=True)
-        self.state_avg = nn.Parameter(th.zeros((state_dim,)), requires_grad=False)
-        self.state_std = nn.Parameter(th.ones((state_dim,)), requires_grad=False)
+        if state_norm:  # the elegantrl nets (AgentPPO.py:348-361); helloworld nets have neither (its :172-178)
+            _init_output_layer(self.net[-1], std=0.1)
+            self.state_avg = nn.Parameter(th.zeros((state_dim,)), requires_grad=False)
+            self.state_std = nn.Parameter(th.ones((state_dim,)), requires_grad=False)
+        else:
+            self.state_avg = self.state_std = None
         self.activation = activation
 
     def forward(self, state: TEN) -> TEN:  # deterministic action for evaluation
@@ -81,12 +86,15 @@ class ActorPPO(nn.Module, _StateNormMixin):
 class CriticPPO(nn.Module, _StateNormMixin):
     """State-value net: V = MLP(state_norm(s))."""
 
-    def __init__(self, net_dims, state_dim: int, action_dim: int, activation: str = "gelu"):
+    def __init__(self, net_dims, state_dim: int, action_dim: int, activation: str = "gelu", state_norm: bool = True):
         super().__init__()
         self.net = make_mlp([state_dim, *net_dims, 1], activation)
-        _init_output_layer(self.net[-1], std=0.5)
-        self.state_avg = nn.Parameter(th.zeros((state_dim,)), requires_grad=False)
-        self.state_std = nn.Parameter(th.ones((state_dim,)), requires_grad=False)
+        if state_norm:
+            _init_output_layer(self.net[-1], std=0.5)
+            self.state_avg = nn.Parameter(th.zeros((state_dim,)), requires_grad=False)
+            self.state_std = nn.Parameter(th.ones((state_dim,)), requires_grad=False)
+        else:
+            self.state_avg = self.state_std = None
         self.activation = activation
 
     def forward(self, state: TEN) -> TEN:

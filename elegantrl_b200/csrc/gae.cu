@@ -78,7 +78,7 @@ __global__ void gae_kernel(float* __restrict__ rewards, uint8_t* __restrict__ un
         }
     }
 
-    double s_all = 0.0, s_lat = 0.0, s_lat2 = 0.0;
+    double s_all = 0.0, s_all2 = 0.0, s_lat = 0.0, s_lat2 = 0.0;
     if (live) {
         // pass 2: scan with the true carry-in, write outputs, fix rewards/undones in place
         float vnext = (t_hi == H) ? last_value[n] : values[(size_t)t_hi * N + n];
@@ -105,31 +105,36 @@ __global__ void gae_kernel(float* __restrict__ rewards, uint8_t* __restrict__ un
                     rsum_out[i] = __fadd_rn(adv, s[u].v);  // reward_sums = advantages + values  (:146)
                     if (!s[u].unmask) { rewards[i] = rf; undones[i] = 0; }
                     s_all += (double)adv;
+                    s_all2 += (double)adv * (double)adv;
                     if (lat_env && (t & 3) == 0) { s_lat += (double)adv; s_lat2 += (double)adv * (double)adv; }
                 }
             }
         }
     }
     // block reduction of the three sums -> one atomicAdd(double) each per CTA
-    __shared__ double red[3][32];
-    s_all = warp_sum(s_all); s_lat = warp_sum(s_lat); s_lat2 = warp_sum(s_lat2);
+    __shared__ double red[4][32];
+    s_all = warp_sum(s_all); s_lat = warp_sum(s_lat); s_lat2 = warp_sum(s_lat2); s_all2 = warp_sum(s_all2);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nwarps = (blockDim.x * blockDim.y + 31) >> 5;
-    if ((tid & 31) == 0) { red[0][tid >> 5] = s_all; red[1][tid >> 5] = s_lat; red[2][tid >> 5] = s_lat2; }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s_all; red[1][tid >> 5] = s_lat; red[2][tid >> 5] = s_lat2; red[3][tid >> 5] = s_all2; }
     __syncthreads();
     if (tid < 32) {
         double a = tid < nwarps ? red[0][tid] : 0.0, b = tid < nwarps ? red[1][tid] : 0.0, c = tid < nwarps ? red[2][tid] : 0.0;
-        a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-        if (tid == 0) { atomicAdd(stat_sums + 0, a); atomicAdd(stat_sums + 1, b); atomicAdd(stat_sums + 2, c); }
+        double d = tid < nwarps ? red[3][tid] : 0.0;
+        a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+        if (tid == 0) { atomicAdd(stat_sums + 0, a); atomicAdd(stat_sums + 1, b); atomicAdd(stat_sums + 2, c); atomicAdd(stat_sums + 3, d); }
     }
 }
 
 __global__ void adv_stats_kernel(const double* stat_sums, double count_all, double count_lat, float* stats_out) {
     // mean over everything; unbiased std over the [::4, ::4] lattice   (reference AgentPPO.py:149)
     double mean = stat_sums[0] / count_all;
-    double m_lat = stat_sums[1] / count_lat;
-    double var = (stat_sums[2] - count_lat * m_lat * m_lat) / (count_lat - 1.0);
+    // count_lat == 0 selects the unbiased std over EVERYTHING (helloworld_PPO_single_file.py:296, adv.std(dim=0))
+    const bool full = count_lat == 0.0;
+    const double cnt = full ? count_all : count_lat;
+    const double m = (full ? stat_sums[0] : stat_sums[1]) / cnt, sq = full ? stat_sums[3] : stat_sums[2];
+    double var = (sq - cnt * m * m) / (cnt - 1.0);
     float sd = (float)sqrt(var > 0.0 ? var : 0.0);
-    if (count_lat < 2.0) sd = nanf("");  // torch .std() of one element is NaN
+    if (cnt < 2.0) sd = nanf("");  // torch .std() of one element is NaN
     stats_out[0] = (float)mean;
     stats_out[1] = sd;
     stats_out[2] = 1.0f / (sd + 1e-5f);

@@ -276,6 +276,7 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
 template <int WM>
 DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, uint64_t draw, float* grads, float* smem,
                      int64_t* s_tn) {
+    float* s_um_mean = reinterpret_cast<float*>(s_tn + UTB);  // one extra scalar behind the index array
     const int H = A.buf.horizon_len, N = A.buf.num_envs;
     // packed mode (horizon_len == 0): `states` points at records {state[S], action[A], unmask, logprob, advantage
     // (already normalised), reward_sum} written by b200rl_pack_minibatches (and all-gathered across ranks); id = record
@@ -334,6 +335,21 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
             }
         }
         s_tn[b] = tn; s_unmask[b] = um; s_logp[b] = lp; s_adv[b] = adv; s_rsum[b] = rs;
+        if (A.hp.flags & B200RL_PPO_CRITIC_MASK_MEAN) {
+            // helloworld's critic weight: the MEAN of unmask over the whole minibatch (its [B] x [B, 1] broadcast)
+            float s = 0.0f;
+            for (int sl = b; sl < A.local_batch; sl += UTB) {
+                if (packed) {
+                    const int64_t r = ids ? ids[sl] : (int64_t)draw * A.local_batch + sl;
+                    s += A.buf.states[r * rec + rec_tail];
+                } else {
+                    const int64_t id = ids ? ids[sl] : sample_index(A.seed, draw, (uint32_t)sl, (uint64_t)H * (uint64_t)N);
+                    s += A.buf.unmasks[(id % H) * N + id / H] ? 1.0f : 0.0f;
+                }
+            }
+            s = warp_sum(s);
+            if (b == 0) *s_um_mean = s / (float)A.local_batch;
+        }
     }
     __syncthreads();
     {
@@ -382,13 +398,25 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
         const int b = threadIdx.x;
         const bool valid = s_tn[b] >= 0;
         const float um = s_unmask[b];
+        const int flags = A.hp.flags;
         if (ni == 1) {
-            // obj_critic = mean(MSE(V(s), reward_sum) * unmask)          (:189-190)
+            // obj_critic = mean(criterion(V(s), reward_sum) * unmask); criterion = MSE (:189-190) or, with
+            // B200RL_PPO_SMOOTH_L1, SmoothL1Loss(beta = 1) (helloworld_PPO_single_file.py:246, 332)
             float err = dzA[UT::elem(0, b)] - s_rsum[b];
-            loss_c = valid ? err * err * um : 0.0f;
-            dzA[UT::elem(0, b)] = valid ? 2.0f * err * um * inv_bsz : 0.0f;
+            float l, dl;
+            if (flags & B200RL_PPO_SMOOTH_L1) {
+                const float ae = fabsf(err);
+                l = ae < 1.0f ? 0.5f * err * err : ae - 0.5f;
+                dl = ae < 1.0f ? err : copysignf(1.0f, err);
+            } else {
+                l = err * err;
+                dl = 2.0f * err;
+            }
+            const float um_c = (flags & B200RL_PPO_CRITIC_MASK_MEAN) ? *s_um_mean : um;
+            loss_c = valid ? l * um_c : 0.0f;
+            dzA[UT::elem(0, b)] = valid ? dl * um_c * inv_bsz : 0.0f;
         } else {
-            // new_logprob, ratio, "clip" factor, entropy                 (:193-203)
+            // new_logprob, ratio, clip, entropy                           (:193-203; helloworld :335-340)
             float logp = 0.0f, ent = 0.0f;
             for (int a = 0; a < OUT; ++a) {
                 float sd = expf(ld_param<WM>(std_log + a));
@@ -397,20 +425,35 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
                 logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
                 ent += 0.5f + kLogSqrt2Pi + lsd;  // 0.5 + 0.5 log(2 pi) + log(scale)
             }
-            float ratio = expf(logp - s_logp[b]);
-            float adv = s_adv[b];
-            float kappa = adv > 0.0f ? 1.0f - A.hp.ratio_clip : 1.0f + A.hp.ratio_clip;
-            float surr = adv * ratio * kappa;
-            loss_s = valid ? surr * um : 0.0f;
-            loss_e = valid ? ent * um : 0.0f;
-            // loss = -(obj_surrogate - lambda_entropy * obj_entropy)
-            float gl = valid ? -(surr * um) * inv_bsz : 0.0f;
+            const float ratio = expf(logp - s_logp[b]);
+            const float adv = s_adv[b];
+            const float um_a = (flags & B200RL_PPO_ACTOR_UNMASKED) ? 1.0f : um;  // helloworld does not mask the actor terms
+            float surr, dsurr_dratio;  // surrogate and its derivative w.r.t. ratio
+            if (flags & B200RL_PPO_MIN_CLIP) {
+                // min(adv * ratio, adv * clamp(ratio, 1 - c, 1 + c))   (helloworld :337-339)
+                const float rc = fminf(fmaxf(ratio, 1.0f - A.hp.ratio_clip), 1.0f + A.hp.ratio_clip);
+                const float s1 = adv * ratio, s2 = adv * rc;
+                const bool take1 = s1 <= s2;  // torch.min passes the gradient to the smaller operand (first on ties)
+                surr = take1 ? s1 : s2;
+                dsurr_dratio = take1 ? adv : ((rc == ratio) ? adv : 0.0f);
+            } else {
+                // the reference's constant-factor "clip": adv * ratio * where(adv > 0, 1 - c, 1 + c)   (:196-199)
+                const float kappa = adv > 0.0f ? 1.0f - A.hp.ratio_clip : 1.0f + A.hp.ratio_clip;
+                surr = adv * ratio * kappa;
+                dsurr_dratio = adv * kappa;
+            }
+            loss_s = valid ? surr * um_a : 0.0f;
+            loss_e = valid ? ent * um_a : 0.0f;
+            // loss = -(obj_surrogate -/+ lambda_entropy * obj_entropy): the reference subtracts the entropy term
+            // (:203-204), helloworld adds it (:340)
+            const float ent_sign = (flags & B200RL_PPO_ENTROPY_BONUS) ? -1.0f : 1.0f;  // sign of d loss / d entropy
+            const float gl = valid ? -(dsurr_dratio * ratio * um_a) * inv_bsz : 0.0f;  // d loss / d new_logprob
             for (int a = 0; a < OUT; ++a) {
                 float sd = expf(ld_param<WM>(std_log + a));
                 float var = sd * sd;
                 float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
                 dzA[UT::elem(a, b)] = gl * diff / var;
-                float dstd = gl * (diff * diff / var - 1.0f) + (valid ? A.hp.lambda_entropy * um * inv_bsz : 0.0f);
+                float dstd = gl * (diff * diff / var - 1.0f) + (valid ? ent_sign * A.hp.lambda_entropy * um_a * inv_bsz : 0.0f);
                 dstd = warp_sum(dstd);  // UTB == 32: exactly warp 0
                 if (b == 0) atomicAdd(g + A.grad_numel[0] - OUT + a, dstd);
             }
@@ -451,7 +494,7 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
     __shared__ float red[32];
-    __shared__ int64_t s_tn[UTB];  // t * N + n of each sample
+    __shared__ int64_t s_tn[UTB + 1];  // t * N + n of each sample (+ one scalar slot)
     __shared__ int s_last;
     const int ni = blockIdx.y;  // the critic and actor updates are disjoint (reference :189-204): concurrent CTAs
     if (A.stage_weights) grads_phase<W_SMEM>(A, blockIdx.x, ni, A.ids, A.draw, A.grads, smem, s_tn);
@@ -478,7 +521,7 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_update_cluster_kernel(const _
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
     __shared__ float red[32];
-    __shared__ int64_t s_tn[UTB];
+    __shared__ int64_t s_tn[UTB + 1];
     __shared__ AdamScalars s_adam;
     cg::cluster_group cluster = cg::this_cluster();
     const int tiles = gridDim.x >> 1;

@@ -68,8 +68,15 @@ typedef struct b200rl_ppo_hyper {
     float ratio_clip;                     /* AgentPPO.ratio_clip (0.25) */
     float lambda_entropy;                 /* AgentPPO.lambda_entropy (0.001) */
     float clip_grad_norm;                 /* Config.clip_grad_norm (3.0); <= 0 disables clipping */
-    int32_t reserved;
+    int32_t flags;                        /* 0 = elegantrl AgentPPO; B200RL_PPO_* bits select the helloworld variant */
 } b200rl_ppo_hyper;
+/* variant bits of b200rl_ppo_hyper.flags -- reference helloworld/helloworld_PPO_single_file.py:319-342, 366-370 */
+#define B200RL_PPO_SMOOTH_L1 1       /* critic criterion SmoothL1Loss (:246) instead of MSELoss */
+#define B200RL_PPO_MIN_CLIP 2        /* surrogate = min(adv*ratio, adv*clamp(ratio, 1-c, 1+c)) (:337-339) */
+#define B200RL_PPO_ENTROPY_BONUS 4   /* objective = surrogate + lambda_entropy * entropy (:340); default subtracts */
+#define B200RL_PPO_ACTOR_UNMASKED 8  /* actor terms are not multiplied by unmask (:339-340) */
+#define B200RL_PPO_CRITIC_MASK_MEAN 16 /* critic loss weighted by mean(unmask) of the minibatch: the [B] x [B, 1]
+                                          broadcast of (:325, 332) averages to mean(loss) * mean(unmask) */
 
 /* The training buffer of AgentPPO.update_net after the GAE pass (reference AgentPPO.py:151):
  * (states, actions, unmasks, logprobs, advantages, reward_sums), time-major [H, N, ...]. */
@@ -147,14 +154,15 @@ B200RL_API int b200rl_rollout_pendulum(const b200rl_rollout_args* args, void* st
 /* AgentPPO.get_advantages (AgentPPO.py:207-232) + reward_sums (:146) + the reduction inputs of the
  * normalisation (:149) in one reverse-scan kernel.  rewards / undones are updated IN PLACE for truncated steps
  * exactly as the reference does (:211-214).  stat_sums (device double[4]) receives {sum(adv), sum over the
- * [::4, ::4] lattice of adv, of adv^2, unused}; the lattice is taken on the GLOBAL env index
+ * [::4, ::4] lattice of adv, of adv^2, sum(adv^2)}; the lattice is taken on the GLOBAL env index
  * env_offset + n so that shards agree.  A multi-GPU caller all-reduces stat_sums before b200rl_adv_stats. */
 B200RL_API int b200rl_gae(float* rewards, uint8_t* undones, const uint8_t* unmasks, const float* values,
                const float* last_value, int32_t horizon_len, int32_t num_envs, float gamma, float lambda_gae,
                int32_t if_use_v_trace, int64_t env_offset, float* advantages, float* reward_sums,
                double* stat_sums, void* stream);
 /* stats_out (device float[4]) = {mean, std_unbiased(lattice), 1 / (std + 1e-5), 0} from the (all-reduced)
- * sums.  count_all = H * N_global; count_lattice = ceil(H/4) * ceil(N_global/4). */
+ * sums.  count_all = H * N_global; count_lattice = ceil(H/4) * ceil(N_global/4), or 0 for the unbiased std over
+ * the whole buffer (helloworld_PPO_single_file.py:296). */
 B200RL_API int b200rl_adv_stats(const double* stat_sums, int64_t count_all, int64_t count_lattice, float* stats_out,
                      void* stream);
 /* advantages = (advantages - mean) / (std + 1e-5) in place (materialises reference AgentPPO.py:149). */

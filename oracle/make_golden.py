@@ -299,3 +299,103 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# --------------------------------------------------------------------------- helloworld variant (BASELINE configs[0])
+def import_helloworld():
+    """Import the reference's helloworld/helloworld_PPO_single_file.py with a stub `gymnasium` (absent here; the
+    file only touches it in its env wrapper and in get_gym_env_args, neither of which the agent arithmetic uses)."""
+    import types
+    gym = types.ModuleType("gymnasium")
+    gym.Wrapper = type("Wrapper", (), {"__init__": lambda self, env=None: setattr(self, "env", env)})
+    gym.make = lambda *a, **k: None
+    spaces = types.ModuleType("gymnasium.spaces")
+    spaces.Discrete, spaces.Box = type("Discrete", (), {}), type("Box", (), {})
+    gym.spaces = spaces
+    sys.modules.setdefault("gymnasium", gym)
+    sys.modules.setdefault("gymnasium.spaces", spaces)
+    sys.path.insert(0, os.path.join(REFERENCE, "helloworld"))
+    import helloworld_PPO_single_file as hw
+    return hw
+
+
+def dump_plain_net(prefix, module, out):
+    linears = [m for m in module.net if isinstance(m, th.nn.Linear)]
+    out[f"{prefix}.n_layers"] = np.int64(len(linears))
+    for i, l in enumerate(linears):
+        out[f"{prefix}.W{i}"] = l.weight.detach().numpy().copy()
+        out[f"{prefix}.b{i}"] = l.bias.detach().numpy().copy()
+    if hasattr(module, "action_std_log"):
+        out[f"{prefix}.action_std_log"] = module.action_std_log.detach().numpy().copy()
+
+
+def case_helloworld(name, state_dim, action_dim, net_dims, horizon_len, seed, **hyper):
+    """helloworld AgentPPO.update_net (helloworld_PPO_single_file.py:283-364) on a synthetic single-env buffer with the
+    minibatch indices replayed: ReLU nets, no state_norm, SmoothL1 critic, min/clamp clip, entropy bonus, no grad clip."""
+    hw = import_helloworld()
+    out = {}
+    th.manual_seed(seed)
+    args = hw.Config(agent_class=hw.AgentPPO, env_class=None,
+                     env_args={'env_name': 'golden', 'state_dim': state_dim, 'action_dim': action_dim, 'if_discrete': False})
+    args.net_dims = list(net_dims)
+    for k, v in hyper.items():
+        setattr(args, k, v)
+    agent = hw.AgentPPO(list(net_dims), state_dim, action_dim, gpu_id=-1, args=args)
+    g = th.Generator().manual_seed(seed + 1)
+    with th.no_grad():
+        agent.act.action_std_log += -0.4 + 0.1 * th.randn(agent.act.action_std_log.shape, generator=g)
+    out["dims"] = np.array([state_dim, action_dim, 1, horizon_len] + list(net_dims), dtype=np.int64)
+    for k in ("gamma", "lambda_gae_adv", "ratio_clip", "learning_rate", "repeat_times"):
+        out[f"hp.{k}"] = np.float64(getattr(agent, k))
+    out["hp.lambda_entropy"] = np.float64(float(agent.lambda_entropy))
+    out["hp.batch_size"] = np.int64(agent.batch_size)
+    dump_plain_net("actor", agent.act, out)
+    dump_plain_net("critic", agent.cri, out)
+
+    states = th.randn((horizon_len, state_dim), generator=g)
+    actions = 0.6 * th.randn((horizon_len, action_dim), generator=g)
+    with th.no_grad():
+        logprobs = agent.act.get_logprob_entropy(states, actions)[0] + 0.05 * th.randn(horizon_len, generator=g)
+    rewards = th.randn((horizon_len, 1), generator=g)
+    terminals = th.rand((horizon_len, 1), generator=g) < 0.06
+    truncates = (th.rand((horizon_len, 1), generator=g) < 0.06) & ~terminals
+    last_state = th.randn(state_dim, generator=g).numpy()
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks"),
+                    (states, actions, logprobs, rewards, ~terminals, ~truncates)):
+        out[f"buf.{k}"] = t.numpy().copy()
+    out["buf.last_state"] = last_state.copy()
+
+    agent.last_state = last_state
+    # run the real thing: update_net does values + GAE + normalisation + all minibatches
+    update_times = int(horizon_len * agent.repeat_times / agent.batch_size)
+    th.manual_seed(seed + 5)
+    ids = th.stack([th.randint(horizon_len, size=(agent.batch_size,)) for _ in range(update_times)])
+    out["update_net.ids"] = ids.numpy()
+    agent2 = copy.deepcopy(agent)
+    th.manual_seed(seed + 5)
+    buf = (states.clone(), actions.clone(), logprobs.clone(), rewards.clone(), (~terminals).clone(), (~truncates).clone())
+    th.set_grad_enabled(False)  # as its train_agent does (helloworld_PPO_single_file.py:491); update_net re-enables it
+    result = agent2.update_net(buf)
+    th.set_grad_enabled(True)
+    out["update_net.result"] = np.array(result, dtype=np.float64)
+    out["update_net.rewards_after"] = buf[3].numpy().copy()
+    out["update_net.undones_after"] = buf[4].numpy().copy()
+    dump_plain_net("update_net.after.actor", agent2.act, out)
+    dump_plain_net("update_net.after.critic", agent2.cri, out)
+    with th.no_grad():
+        out["values"] = agent.cri(states).squeeze(1).numpy()
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main_helloworld():
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    # helloworld Pendulum recipe (helloworld_PPO_single_file.py:535-557): net_dims [64, 32], gamma 0.97, repeat 16
+    case_helloworld("helloworld_s3_a1_64x32", 3, 1, (64, 32), horizon_len=96, seed=71, gamma=0.97, repeat_times=4,
+                    batch_size=32, learning_rate=3e-4, lambda_entropy=0.01)
+    case_helloworld("helloworld_s8_a2_64x64", 8, 2, (64, 64), horizon_len=64, seed=73, repeat_times=2, batch_size=64)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "helloworld"):
+    main_helloworld()

@@ -238,10 +238,13 @@ def advantage_stats(advantages):
     return mean, std
 
 
-def normalize_advantages(advantages):
-    """(adv - adv.mean()) / (adv[::4, ::4].std() + 1e-5) -- reference AgentPPO.py:149."""
+def normalize_advantages(advantages, full_std=False):
+    """(adv - adv.mean()) / (adv[::4, ::4].std() + 1e-5) -- reference AgentPPO.py:149; full_std: the helloworld
+    variant (adv - mean) / (adv.std() + 1e-5), helloworld_PPO_single_file.py:296."""
     dt = advantages.dtype
     mean, std = advantage_stats(advantages)
+    if full_std:
+        std = advantages.std(ddof=1, dtype=np.float64)
     return ((advantages - dt.type(mean)) / (dt.type(std) + dt.type(1e-5))).astype(dt)
 
 
@@ -315,8 +318,20 @@ def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
     xc = state_norm(critic, state)
     value, acts_c, pre_c = mlp_forward(critic, xc, keep=True)
     err = value[:, 0] - batch["reward_sum"]
-    obj_critic = (err * err * unmask).mean(dtype=dt)
-    d_value = (dt.type(2.0) * err * unmask / bsz)[:, None].astype(dt)
+    if hp.get("critic_loss", "mse") == "smooth_l1":  # helloworld_PPO_single_file.py:246 SmoothL1Loss(beta=1)
+        small = np.abs(err) < 1
+        loss_el = np.where(small, dt.type(0.5) * err * err, np.abs(err) - dt.type(0.5)).astype(dt)
+        d_el = np.where(small, err, np.sign(err)).astype(dt)
+    else:
+        loss_el, d_el = err * err, dt.type(2.0) * err
+    if hp.get("critic_mask", "elementwise") == "batch_mean":
+        # helloworld multiplies criterion(...) [B] by unmask [B, 1]: a [B, B] outer product whose mean is
+        # mean(loss) * mean(unmask)  (helloworld_PPO_single_file.py:325, 332)
+        um_c = np.full_like(unmask, unmask.mean(dtype=dt))
+    else:
+        um_c = unmask
+    obj_critic = (loss_el * um_c).mean(dtype=dt)
+    d_value = (d_el * um_c / bsz)[:, None].astype(dt)
     dWc, dbc, _ = mlp_backward(critic, acts_c, pre_c, d_value)
     gc = [g for pair in zip(dWc, dbc) for g in pair]
     gc, norm_c = clip_grads(gc, hp["clip_grad_norm"])
@@ -332,16 +347,26 @@ def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
     entropy = gaussian_entropy(std_log, state.shape[0], dt)
     ratio = np.exp(new_logprob - batch["logprob"])
     adv = batch["advantage"]
-    kappa = np.where(adv > 0, dt.type(1 - hp["ratio_clip"]), dt.type(1 + hp["ratio_clip"])).astype(dt)
-    surrogate = adv * ratio * kappa
-    obj_surrogate = (surrogate * unmask).mean(dtype=dt)
-    obj_entropy = (entropy * unmask).mean(dtype=dt)
+    mask_a = unmask if hp.get("mask_actor", True) else np.ones_like(unmask)  # helloworld does not mask the actor terms
+    if hp.get("surrogate", "factor") == "min_clip":  # helloworld_PPO_single_file.py:337-339
+        clipped = np.clip(ratio, dt.type(1 - hp["ratio_clip"]), dt.type(1 + hp["ratio_clip"]))
+        s1, s2 = adv * ratio, adv * clipped
+        take1 = s1 <= s2
+        surrogate = np.where(take1, s1, s2).astype(dt)
+        d_ratio = np.where(take1, adv, np.where(clipped == ratio, adv, dt.type(0))).astype(dt)
+    else:  # the reference's constant factor, AgentPPO.py:196-199
+        kappa = np.where(adv > 0, dt.type(1 - hp["ratio_clip"]), dt.type(1 + hp["ratio_clip"])).astype(dt)
+        surrogate = adv * ratio * kappa
+        d_ratio = (adv * kappa).astype(dt)
+    obj_surrogate = (surrogate * mask_a).mean(dtype=dt)
+    obj_entropy = (entropy * mask_a).mean(dtype=dt)
+    ent_sign = dt.type(-1.0 if hp.get("entropy_bonus", False) else 1.0)  # d loss / d entropy: helloworld ADDS the bonus
     lam_ent = dt.type(hp["lambda_entropy"])
     # loss = -(obj_surrogate - obj_entropy * lambda_entropy)
-    g_logp = (-(surrogate * unmask) / bsz).astype(dt)                      # d loss / d new_logprob
+    g_logp = (-(d_ratio * ratio * mask_a) / bsz).astype(dt)                 # d loss / d new_logprob
     d_mean = (g_logp[:, None] * diff / var).astype(dt)                      # d logp / d mu = (a - mu) / var
     d_std_log = (g_logp[:, None] * (diff * diff / var - dt.type(1.0))).sum(axis=0, keepdims=True) \
-        + lam_ent * unmask.mean(dtype=dt)                                   # d entropy / d std_log = 1
+        + ent_sign * lam_ent * mask_a.mean(dtype=dt)                        # d entropy / d std_log = 1
     dWa, dba, _ = mlp_backward(actor, acts_a, pre_a, d_mean)
     ga = [g for pair in zip(dWa, dba) for g in pair] + [d_std_log.astype(dt)]
     ga, norm_a = clip_grads(ga, hp["clip_grad_norm"])
@@ -465,3 +490,31 @@ def stats_from_sums(sums, count_all, count_lattice):
     m_lat = sums[1] / count_lattice
     var = (sums[2] - count_lattice * m_lat * m_lat) / (count_lattice - 1.0)
     return mean, math.sqrt(max(var, 0.0))
+
+
+# ------------------------------------------------------------------------------- helloworld variant
+HELLOWORLD_FLAVOUR = dict(critic_loss="smooth_l1", critic_mask="batch_mean", surrogate="min_clip", entropy_bonus=True,
+                          mask_actor=False, clip_grad_norm=0.0)
+
+
+def update_net_helloworld(actor, critic, opt_a, opt_c, buf, last_state, ids_per_update, hp):
+    """helloworld AgentPPO.update_net -- reference helloworld/helloworld_PPO_single_file.py:283-364: single-env buffer
+    (states [H, S], actions [H, A], logprobs [H], rewards / undones / unmasks [H, 1]), ReLU nets without state_norm,
+    full-buffer std in the advantage normalisation (:296), SmoothL1 critic (:246, 332), min/clamp clip (:337-339),
+    entropy bonus ADDED (:340), actor terms not masked, no grad clipping (:366-370).
+    Returns (obj_critic_avg, obj_actor_avg, 0.0) as :314-317 (its a_std_log attribute does not exist -> 0)."""
+    states, actions, logprobs, rewards, undones, unmasks = buf
+    hp = dict(hp, **HELLOWORLD_FLAVOUR)
+    values = critic_value(critic, states)                                   # [H]
+    last_value = critic_value(critic, last_state[None, :])                  # [1]
+    advantages = gae(rewards, undones, unmasks, values[:, None], last_value, hp["gamma"], hp["lambda_gae_adv"], True)
+    reward_sums = (advantages + values[:, None]).astype(values.dtype)
+    adv_norm = normalize_advantages(advantages, full_std=True)
+    buffer = dict(states=states[:, None, :], actions=actions[:, None, :], unmasks=unmasks, logprobs=logprobs[:, None],
+                  advantages=adv_norm, reward_sums=reward_sums)
+    logs = []
+    for ids in ids_per_update:
+        (obj_c, obj_s, obj_e), _ = ppo_minibatch(actor, critic, opt_a, opt_c, gather_minibatch(buffer, ids), hp)
+        logs.append((obj_c, obj_s + obj_e * hp["lambda_entropy"]))
+    logs = np.array(logs, dtype=np.float64)
+    return (logs[:, 0].mean(), logs[:, 1].mean(), 0.0), dict(values=values, advantages=advantages, adv_norm=adv_norm)

@@ -40,3 +40,23 @@ def flat_params(net):
     if "action_std_log" in net:
         out.append(net["action_std_log"])
     return out
+
+
+HELLOWORLD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "helloworld_*.npz")))
+
+
+def plain_net_of(g, prefix, dtype=np.float32):
+    """helloworld nets: ReLU, no state_norm (reference helloworld/helloworld_PPO_single_file.py:172-212)."""
+    n_layers = int(g[f"{prefix}.n_layers"])
+    net = {"W": [g[f"{prefix}.W{i}"].astype(dtype).copy() for i in range(n_layers)],
+           "b": [g[f"{prefix}.b{i}"].astype(dtype).copy() for i in range(n_layers)],
+           "state_avg": None, "state_std": None, "activation": "relu"}
+    if f"{prefix}.action_std_log" in g:
+        net["action_std_log"] = g[f"{prefix}.action_std_log"].astype(dtype).copy()
+    return net
+
+
+def helloworld_hyper_of(g):
+    return dict(gamma=float(g["hp.gamma"]), lambda_gae_adv=float(g["hp.lambda_gae_adv"]), ratio_clip=float(g["hp.ratio_clip"]),
+                lambda_entropy=float(g["hp.lambda_entropy"]), learning_rate=float(g["hp.learning_rate"]),
+                batch_size=int(g["hp.batch_size"]), repeat_times=float(g["hp.repeat_times"]))

@@ -482,3 +482,70 @@ def test_packed_minibatches_equal_direct_gather(case, update_impl):
         got, ref = gu.flat_params(G.module_to_net(module)), gu.flat_params(gu.net_of(g, f"update.after.{which}"))
         for a, b in zip(got, ref):
             G.assert_close(a, b, RTOL, 2e-6, which)
+
+
+# ------------------------------------------------------------------------------- helloworld variant
+@pytest.mark.parametrize("case", gu.HELLOWORLD_CASES)
+def test_helloworld_agent_against_reference(case, update_impl):
+    """elegantrl_b200.agents.helloworld.AgentPPO (same kernels, variant flags) against the tutorial's
+    helloworld_PPO_single_file.AgentPPO.update_net: ReLU nets without state_norm, full-buffer std, SmoothL1 critic with
+    the mean(unmask) weight, min/clamp clip, entropy bonus, no grad clipping, 2-D single-env buffer."""
+    from elegantrl_b200 import Config
+    from elegantrl_b200.agents import helloworld
+    g = gu.load(case)
+    hp = gu.helloworld_hyper_of(g)
+    dims = [int(x) for x in g["dims"]]
+    args = Config()
+    for k in ("gamma", "lambda_gae_adv", "ratio_clip", "lambda_entropy", "learning_rate", "batch_size", "repeat_times"):
+        setattr(args, k, hp[k])
+    agent = helloworld.AgentPPO(dims[4:], dims[0], dims[1], gpu_id=0, args=args)
+    for module, prefix in ((agent.act, "actor"), (agent.cri, "critic")):
+        net = gu.plain_net_of(g, prefix)
+        linears = [m for m in module.net if isinstance(m, th.nn.Linear)]
+        with th.no_grad():
+            for layer, w, b in zip(linears, net["W"], net["b"]):
+                layer.weight.copy_(th.from_numpy(w)); layer.bias.copy_(th.from_numpy(b))
+            if "action_std_log" in net:
+                module.action_std_log.copy_(th.from_numpy(net["action_std_log"]))
+    buffer = [G.cuda(g[f"buf.{k}"]) for k in ("states", "actions", "logprobs", "rewards", "undones", "unmasks")]
+    agent.last_state = g["buf.last_state"]          # numpy, as the tutorial keeps it
+    agent._inject_ids = G.cuda(g["update_net.ids"])
+    result = agent.update_net(buffer)
+    G.assert_close(np.array(result), g["update_net.result"], RTOL, 1e-6)
+    G.assert_close(buffer[3], g["update_net.rewards_after"], RTOL, 2e-6)
+    assert np.array_equal(buffer[4].cpu().numpy(), g["update_net.undones_after"])
+    G.assert_close(agent.last_update_info["values"].reshape(-1), g["values"], RTOL, 2e-6)
+    for which, module in (("actor", agent.act), ("critic", agent.cri)):
+        got = gu.flat_params(po.net_from_torch(module))
+        ref = gu.flat_params(gu.plain_net_of(g, f"update_net.after.{which}"))
+        for a, b in zip(got, ref):
+            G.assert_close(a, b, RTOL, 2e-6, which)
+    assert isinstance(agent.last_state, np.ndarray)
+
+
+def test_helloworld_agent_rollout_plumbing():
+    """Tutorial loop shape contract (helloworld_PPO_single_file.py:248-277, 490-517) with a numpy gym-style env."""
+    from elegantrl_b200 import Config
+    from elegantrl_b200.agents import helloworld
+
+    class NumpyPendulum:  # gym-style single env: numpy in / out, (state, reward, terminal, truncate, info)
+        def __init__(self):
+            from elegantrl_b200.envs import PendulumVecEnv
+            self.inner = PendulumVecEnv(num_envs=1, gpu_id=-1, max_step=30, seed=1)
+        def reset(self):
+            return self.inner.reset()[0][0].numpy(), {}
+        def step(self, action):
+            s, r, te, tr, _ = self.inner.step(th.as_tensor(action, dtype=th.float32).reshape(1, 1))
+            return s[0].numpy(), float(r[0]), bool(te[0]), bool(tr[0]), {}
+
+    args = Config()
+    args.batch_size, args.repeat_times, args.gamma = 32, 4, 0.97
+    agent = helloworld.AgentPPO([64, 32], 3, 1, gpu_id=0, args=args)
+    env = NumpyPendulum()
+    agent.last_state = env.reset()[0]
+    buf = agent.explore_env(env, 64)
+    shapes = [tuple(t.shape) for t in buf]
+    assert shapes == [(64, 3), (64, 1), (64,), (64, 1), (64, 1), (64, 1)]
+    assert float(buf[2].abs().max()) == 0.0 and buf[4].dtype == th.bool and int((~buf[5]).sum()) == 2
+    res = agent.update_net(buf)
+    assert len(res) == 3 and np.isfinite(res[:2]).all() and res[2] == 0.0

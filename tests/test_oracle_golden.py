@@ -123,3 +123,21 @@ def test_rollout(case):
     assert np.array_equal(out["cur_step"], g["rollout.cur_step"])
     np.testing.assert_allclose(out["last_state"], g["rollout.last_state"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(out["values"], g["gae.values"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", gu.HELLOWORLD_CASES)
+def test_helloworld_update_net(case):
+    """The helloworld flavour of the oracle against helloworld_PPO_single_file.AgentPPO.update_net."""
+    g = gu.load(case)
+    hp = gu.helloworld_hyper_of(g)
+    actor, critic = gu.plain_net_of(g, "actor"), gu.plain_net_of(g, "critic")
+    opt_a, opt_c = po.new_adam_state(actor, True), po.new_adam_state(critic, False)
+    buf = [g[f"buf.{k}"].copy() for k in ("states", "actions", "logprobs", "rewards", "undones", "unmasks")]
+    result, info = po.update_net_helloworld(actor, critic, opt_a, opt_c, buf, g["buf.last_state"], g["update_net.ids"], hp)
+    np.testing.assert_allclose(info["values"], g["values"], **F32)
+    np.testing.assert_allclose(result, g["update_net.result"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(buf[3], g["update_net.rewards_after"], **F32)
+    assert np.array_equal(buf[4], g["update_net.undones_after"])
+    for prefix, net in (("actor", actor), ("critic", critic)):
+        for mine, ref in zip(gu.flat_params(net), gu.flat_params(gu.plain_net_of(g, f"update_net.after.{prefix}"))):
+            np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=2e-6)
