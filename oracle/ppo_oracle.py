@@ -427,7 +427,7 @@ def net_from_torch(module, dtype=np.float32):
     net = {"W": [l.weight.detach().cpu().numpy().astype(dtype).copy() for l in linears],
            "b": [l.bias.detach().cpu().numpy().astype(dtype).copy() for l in linears],
            "activation": activation, "state_avg": None, "state_std": None}
-    if hasattr(module, "state_avg"):
+    if getattr(module, "state_avg", None) is not None:
         net["state_avg"] = module.state_avg.detach().cpu().numpy().astype(dtype).copy()
         net["state_std"] = module.state_std.detach().cpu().numpy().astype(dtype).copy()
     if hasattr(module, "action_std_log"):
