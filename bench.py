@@ -111,17 +111,23 @@ class ClockSampler:
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path (oracle/cpu_port.py restates its ATen op sequence), all host
-    threads, same config / metric; rank 0 only."""
+    """The reference's CPU implementation of the path (oracle/cpu_port.py restates its ATen op sequence) on the host
+    cores, same config / metric; rank 0 only.  Thread count: calibrated (torch's default of one thread per core is
+    several times SLOWER than 8-16 threads on these tiny ops).  Each step is a full cycle at 65 536 envs unless K + W
+    such cycles would not fit in ~3 minutes; then every step is the same cycle on a power-of-two subset of the envs."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch as th
-    from oracle.cpu_port import CpuPPO
+    from oracle.cpu_port import CpuPPO, best_thread_count
     from elegantrl_b200.envs import PendulumVecEnv
-    threads = th.get_num_threads()
+    threads, scores = best_thread_count(NET_DIMS, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+    budget_s, num_envs = 180.0, NUM_ENVS
+    est_full = NUM_ENVS * HORIZON / scores[threads]          # seconds per full cycle, from the calibration run
+    while num_envs > 4096 and (args.warmup + args.steps) * est_full * num_envs / NUM_ENVS > budget_s:
+        num_envs //= 2
     th.manual_seed(0)
-    agent = CpuPPO(NET_DIMS, 3, 1, NUM_ENVS, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
-    env = PendulumVecEnv(num_envs=NUM_ENVS, gpu_id=-1, max_step=200, seed=0)
+    agent = CpuPPO(NET_DIMS, 3, 1, num_envs, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+    env = PendulumVecEnv(num_envs=num_envs, gpu_id=-1, max_step=200, seed=0)
     agent.last_state = env.reset()[0]
     times = []
     for i in range(args.warmup + args.steps):
@@ -131,11 +137,14 @@ def run_reference(args):
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = NUM_ENVS * HORIZON * len(times) / total
-    sample = f"{len(times)} full cycles (65 536 envs x 128 steps + update) after {args.warmup} warm-up, {threads} torch threads"
+    value = num_envs * HORIZON * len(times) / total
+    sample = (f"{len(times)} cycles of {num_envs} envs x {HORIZON} steps + update after {args.warmup} warm-up; {threads} torch "
+              f"threads chosen by calibration {({t: round(v / 1e6, 2) for t, v in scores.items()})} M env-steps/s")
+    cfg = workload_config(1)
+    cfg["reference_sample_envs"] = num_envs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -280,11 +289,13 @@ def run_engine(args):
             "gpu_launches": int(launches), "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_port import time_cpu_cycles
-        cb = time_cpu_cycles(NUM_ENVS, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, batch_size=BATCH_SIZE,
-                             repeat_times=REPEAT_TIMES)
+        from oracle.cpu_port import best_thread_count, time_cpu_cycles
+        threads, _ = best_thread_count(NET_DIMS, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+        cb = time_cpu_cycles(NUM_ENVS, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, threads=threads,
+                             batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
         line["cpu_baseline"] = {"value": cb["env_steps_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
-                                "sample": f"{cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up; "
+                                "sample": f"{cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up, thread count "
+                                          f"calibrated ({cb['threads']} of {os.cpu_count()} logical CPUs); "
                                           f"explore {statistics.mean(cb['explore_s']):.3f}s + update {statistics.mean(cb['update_s']):.3f}s per cycle"}
     if rank == 0:
         print(json.dumps(line), flush=True)

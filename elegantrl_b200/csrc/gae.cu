@@ -84,16 +84,21 @@ __global__ void gae_kernel(float* __restrict__ rewards, uint8_t* __restrict__ un
         float vnext = (t_hi == H) ? last_value[n] : values[(size_t)t_hi * N + n];
         float y = y_in;
         const bool lat_env = ((env_offset + n) & 3) == 0;
-        for (int t1 = t_hi; t1 > t_lo; t1 -= kUnroll) {
-            StepIn s[kUnroll];
+        // software pipeline: the loads of the next kUnroll time steps are in flight while this batch is scanned
+        StepIn s[kUnroll], nx[kUnroll];
+        auto load_batch = [&](StepIn (&dst)[kUnroll], int t1) {
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 int t = t1 - 1 - u;
                 if (t >= t_lo) {
                     size_t i = (size_t)t * N + n;
-                    s[u] = StepIn{rewards[i], values[i], undones[i] != 0, unmasks[i] != 0};
+                    dst[u] = StepIn{rewards[i], values[i], undones[i] != 0, unmasks[i] != 0};
                 }
             }
+        };
+        load_batch(s, t_hi);
+        for (int t1 = t_hi; t1 > t_lo; t1 -= kUnroll) {
+            if (t1 - kUnroll > t_lo) load_batch(nx, t1 - kUnroll);
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 int t = t1 - 1 - u;
@@ -109,6 +114,8 @@ __global__ void gae_kernel(float* __restrict__ rewards, uint8_t* __restrict__ un
                     if (lat_env && (t & 3) == 0) { s_lat += (double)adv; s_lat2 += (double)adv * (double)adv; }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) s[u] = nx[u];
         }
     }
     // block reduction of the three sums -> one atomicAdd(double) each per CTA
