@@ -42,7 +42,7 @@ DEV float gae_step(const StepIn& s, float gamma, float lam, float& y, float& vne
 }
 
 template <bool VTRACE>
-__global__ void gae_kernel(float* __restrict__ rewards, uint8_t* __restrict__ undones,
+__global__ void __launch_bounds__(512) gae_kernel(float* __restrict__ rewards, uint8_t* __restrict__ undones,
                            const uint8_t* __restrict__ unmasks, const float* __restrict__ values,
                            const float* __restrict__ last_value, int H, int N, float gamma, float lam,
                            int64_t env_offset, float* __restrict__ adv_out, float* __restrict__ rsum_out,
@@ -178,7 +178,7 @@ int b200rl_gae(float* rewards, uint8_t* undones, const uint8_t* unmasks, const f
     int chunks = 1;
     if (num_envs < 148 * 256) {
         int64_t want = (148LL * 512) / (num_envs > 0 ? num_envs : 1);  // threads we would like / env
-        while (chunks < 32 && chunks * 2 <= want && horizon_len / (chunks * 2) >= 8 && bx * chunks * 2 <= 1024) chunks *= 2;
+        while (chunks < 32 && chunks * 2 <= want && horizon_len / (chunks * 2) >= 8 && bx * chunks * 2 <= 512) chunks *= 2;
     }
     dim3 block(bx, chunks), grid((num_envs + bx - 1) / bx);
     size_t smem = chunks > 1 ? (size_t)chunks * bx * sizeof(float2) : 0;
