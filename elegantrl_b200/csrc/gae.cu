@@ -132,6 +132,105 @@ __global__ void __launch_bounds__(512) gae_kernel(float* __restrict__ rewards, u
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Large-N variant of the sequential scan: same thread <-> env mapping and the same op order (bit-exact with the
+// reference), but the four input streams are staged through shared memory by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx): one elected thread keeps a whole batch of kStage time steps (20 KB per CTA)
+// in flight ahead of the scan, which the register-prefetch kernel above cannot afford (it is latency-bound at ~14 %
+// of DRAM throughput, profiles/r01_gae_*).  Requires 128 envs per CTA and N % 128 == 0 (16-byte aligned row segments).
+constexpr int kGaeEnvs = 128;
+constexpr int kStage = 16;
+struct __align__(128) GaeStage {
+    float r[kStage][kGaeEnvs];
+    float v[kStage][kGaeEnvs];
+    uint8_t ud[kStage][kGaeEnvs];
+    uint8_t um[kStage][kGaeEnvs];
+};
+
+DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+template <bool VTRACE>
+__global__ void __launch_bounds__(kGaeEnvs) gae_tma_kernel(float* __restrict__ rewards, uint8_t* __restrict__ undones,
+                                                           const uint8_t* __restrict__ unmasks, const float* __restrict__ values,
+                                                           const float* __restrict__ last_value, int H, int N, float gamma,
+                                                           float lam, int64_t env_offset, float* __restrict__ adv_out,
+                                                           float* __restrict__ rsum_out, double* stat_sums) {
+    __shared__ GaeStage stage[2];
+    __shared__ uint64_t full[2];
+    const int n0 = blockIdx.x * kGaeEnvs, n = n0 + threadIdx.x;
+    const int nb = (H + kStage - 1) / kStage;
+
+    auto issue = [&](int k) {  // batch k covers t in [t_lo, t_hi), scanning downwards from H
+        const int t_hi = H - k * kStage, t_lo = max(0, t_hi - kStage), rows = t_hi - t_lo;
+        GaeStage& st = stage[k & 1];
+        uint64_t* bar = &full[k & 1];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((uint32_t)(rows * 1280)) : "memory");
+        for (int j = 0; j < rows; ++j) {
+            const size_t g = (size_t)(t_lo + j) * N + n0;
+            bulk_g2s(st.r[j], rewards + g, 512, bar);
+            bulk_g2s(st.v[j], values + g, 512, bar);
+            bulk_g2s(st.ud[j], undones + g, 128, bar);
+            bulk_g2s(st.um[j], unmasks + g, 128, bar);
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0);
+        if (nb > 1) issue(1);
+    }
+    __syncthreads();
+
+    float vnext = last_value[n];
+    float y = 0.0f;
+    double s_all = 0.0, s_all2 = 0.0, s_lat = 0.0, s_lat2 = 0.0;
+    const bool lat_env = ((env_offset + n) & 3) == 0;
+    for (int k = 0; k < nb; ++k) {
+        const int t_hi = H - k * kStage, t_lo = max(0, t_hi - kStage);
+        const uint32_t parity = (k >> 1) & 1;
+        {   // wait for the batch
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 10000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_addr(&full[k & 1])), "r"(parity) : "memory");
+            }
+        }
+        const GaeStage& st = stage[k & 1];
+#pragma unroll 4
+        for (int t = t_hi - 1; t >= t_lo; --t) {
+            const int j = t - t_lo;
+            const size_t i = (size_t)t * N + n;
+            StepIn in{st.r[j][threadIdx.x], st.v[j][threadIdx.x], st.ud[j][threadIdx.x] != 0, st.um[j][threadIdx.x] != 0};
+            float rf; bool uf;
+            const float adv = gae_step<VTRACE>(in, gamma, lam, y, vnext, rf, uf);
+            adv_out[i] = adv;
+            rsum_out[i] = __fadd_rn(adv, in.v);
+            if (!in.unmask) { rewards[i] = rf; undones[i] = 0; }
+            s_all += (double)adv;
+            s_all2 += (double)adv * (double)adv;
+            if (lat_env && (t & 3) == 0) { s_lat += (double)adv; s_lat2 += (double)adv * (double)adv; }
+        }
+        __syncthreads();  // everyone is done with stage[k & 1]
+        if (threadIdx.x == 0 && k + 2 < nb) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async-proxy overwrite
+            issue(k + 2);
+        }
+    }
+    __shared__ double red[4][4];
+    s_all = warp_sum(s_all); s_lat = warp_sum(s_lat); s_lat2 = warp_sum(s_lat2); s_all2 = warp_sum(s_all2);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = s_all; red[1][w] = s_lat; red[2][w] = s_lat2; red[3][w] = s_all2; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const double tot = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        atomicAdd(stat_sums + threadIdx.x, tot);
+    }
+}
+
 __global__ void adv_stats_kernel(const double* stat_sums, double count_all, double count_lat, float* stats_out) {
     // mean over everything; unbiased std over the [::4, ::4] lattice   (reference AgentPPO.py:149)
     double mean = stat_sums[0] / count_all;
@@ -179,6 +278,19 @@ int b200rl_gae(float* rewards, uint8_t* undones, const uint8_t* unmasks, const f
     if (num_envs < 148 * 256) {
         int64_t want = (148LL * 512) / (num_envs > 0 ? num_envs : 1);  // threads we would like / env
         while (chunks < 32 && chunks * 2 <= want && horizon_len / (chunks * 2) >= 8 && bx * chunks * 2 <= 512) chunks *= 2;
+    }
+    if (chunks == 1 && (num_envs % kGaeEnvs) == 0 && num_envs >= 148 * 64 && horizon_len >= 2 * kStage) {
+        // TMA-staged sequential scan (bit-exact, bandwidth-oriented)
+        const unsigned g = num_envs / kGaeEnvs;
+        if (if_use_v_trace)
+            gae_tma_kernel<true><<<g, kGaeEnvs, 0, stream>>>(rewards, undones, unmasks, values, last_value, horizon_len, num_envs,
+                                                            gamma, lambda_gae, env_offset, advantages, reward_sums, stat_sums);
+        else
+            gae_tma_kernel<false><<<g, kGaeEnvs, 0, stream>>>(rewards, undones, unmasks, values, last_value, horizon_len, num_envs,
+                                                             gamma, lambda_gae, env_offset, advantages, reward_sums, stat_sums);
+        B200RL_CHECK_CUDA(cudaGetLastError());
+        B200RL_COUNT_LAUNCH(1);
+        return 0;
     }
     dim3 block(bx, chunks), grid((num_envs + bx - 1) / bx);
     size_t smem = chunks > 1 ? (size_t)chunks * bx * sizeof(float2) : 0;
