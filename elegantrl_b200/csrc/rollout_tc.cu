@@ -94,53 +94,62 @@ DEV float eval_net(GroupCtx& c, const float (&x)[3], int lane) {
     const float* sm = c.small;
     constexpr uint32_t idesc = tc05::make_idesc_tf32(kTileRows, kHid);
     const float2 x2[3] = {splat(x[0]), splat(x[1]), splat(x[2])};
-#pragma unroll 2
-    for (int ch = 0; ch < kChunks; ++ch) {
-        const int s = ch & 1;
-        const uint32_t use = c.evals * 4 + (ch >> 1);  // how often slot s has been filled before
-        float2 hi[4], lo[4];
+    // 4 rounds of 16 hidden units: two 8-column chunks are produced back to back into the two ring slots, then ONE
+    // proxy fence + arrival covers both and the last-arriving warp issues the 6 MMAs of the two K-steps
+#pragma unroll 1
+    for (int cp = 0; cp < kChunks / 2; ++cp) {
+        const uint32_t use = c.evals * (kChunks / 2) + cp;  // how often the slot pair has been filled before
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = ch * 8 + h * 4;
-            const float4 b = *reinterpret_cast<const float4*>(sm + kB1 + j);
-            const float4 w0 = *reinterpret_cast<const float4*>(sm + kW1t + j);
-            const float4 w1 = *reinterpret_cast<const float4*>(sm + kW1t + 64 + j);
-            const float4 w2 = *reinterpret_cast<const float4*>(sm + kW1t + 128 + j);
-            float2 a01 = __ffma2_rn(x2[0], make_float2(w0.x, w0.y), make_float2(b.x, b.y));
-            float2 a23 = __ffma2_rn(x2[0], make_float2(w0.z, w0.w), make_float2(b.z, b.w));
-            a01 = __ffma2_rn(x2[1], make_float2(w1.x, w1.y), a01);
-            a23 = __ffma2_rn(x2[1], make_float2(w1.z, w1.w), a23);
-            a01 = __ffma2_rn(x2[2], make_float2(w2.x, w2.y), a01);
-            a23 = __ffma2_rn(x2[2], make_float2(w2.z, w2.w), a23);
-            const float2 g01 = gelu_fast2(a01), g23 = gelu_fast2(a23);
-            hi[h * 2 + 0] = make_float2(tc05::tf32_hi(g01.x), tc05::tf32_hi(g01.y));
-            hi[h * 2 + 1] = make_float2(tc05::tf32_hi(g23.x), tc05::tf32_hi(g23.y));
-            lo[h * 2 + 0] = __ffma2_rn(hi[h * 2 + 0], splat(-1.0f), g01);
-            lo[h * 2 + 1] = __ffma2_rn(hi[h * 2 + 1], splat(-1.0f), g23);
+        for (int half = 0; half < 2; ++half) {
+            const int ch = cp * 2 + half;
+            float2 hi[4], lo[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = ch * 8 + h * 4;
+                const float4 b = *reinterpret_cast<const float4*>(sm + kB1 + j);
+                const float4 w0 = *reinterpret_cast<const float4*>(sm + kW1t + j);
+                const float4 w1 = *reinterpret_cast<const float4*>(sm + kW1t + 64 + j);
+                const float4 w2 = *reinterpret_cast<const float4*>(sm + kW1t + 128 + j);
+                float2 a01 = __ffma2_rn(x2[0], make_float2(w0.x, w0.y), make_float2(b.x, b.y));
+                float2 a23 = __ffma2_rn(x2[0], make_float2(w0.z, w0.w), make_float2(b.z, b.w));
+                a01 = __ffma2_rn(x2[1], make_float2(w1.x, w1.y), a01);
+                a23 = __ffma2_rn(x2[1], make_float2(w1.z, w1.w), a23);
+                a01 = __ffma2_rn(x2[2], make_float2(w2.x, w2.y), a01);
+                a23 = __ffma2_rn(x2[2], make_float2(w2.z, w2.w), a23);
+                const float2 g01 = gelu_fast2(a01), g23 = gelu_fast2(a23);
+                hi[h * 2 + 0] = make_float2(tc05::tf32_hi(g01.x), tc05::tf32_hi(g01.y));
+                hi[h * 2 + 1] = make_float2(tc05::tf32_hi(g23.x), tc05::tf32_hi(g23.y));
+                lo[h * 2 + 0] = __ffma2_rn(hi[h * 2 + 0], splat(-1.0f), g01);
+                lo[h * 2 + 1] = __ffma2_rn(hi[h * 2 + 1], splat(-1.0f), g23);
+            }
+            // the MMAs that read the previous content of the slot pair must be done before it is overwritten
+            if (half == 0 && use > 0) tc05::mbar_wait(&c.slot_free[0], (use - 1) & 1);
+            const uint32_t slot = c.ring_addr + half * kSlotBytes + c.row_off;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "f"(hi[0].x), "f"(hi[0].y), "f"(hi[1].x), "f"(hi[1].y) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 128), "f"(hi[2].x), "f"(hi[2].y), "f"(hi[3].x), "f"(hi[3].y) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096), "f"(lo[0].x), "f"(lo[0].y), "f"(lo[1].x), "f"(lo[1].y) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096 + 128), "f"(lo[2].x), "f"(lo[2].y), "f"(lo[3].x), "f"(lo[3].y) : "memory");
         }
-        // the MMAs that read the previous content of slot s must be done before it is overwritten
-        if (use > 0) tc05::mbar_wait(&c.slot_free[s], (use - 1) & 1);
-        const uint32_t slot = c.ring_addr + s * kSlotBytes + c.row_off;
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "f"(hi[0].x), "f"(hi[0].y), "f"(hi[1].x), "f"(hi[1].y) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 128), "f"(hi[2].x), "f"(hi[2].y), "f"(hi[3].x), "f"(hi[3].y) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096), "f"(lo[0].x), "f"(lo[0].y), "f"(lo[1].x), "f"(lo[1].y) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 4096 + 128), "f"(lo[2].x), "f"(lo[2].y), "f"(lo[3].x), "f"(lo[3].y) : "memory");
         tc05::fence_proxy_async_smem();
         __syncwarp();
-        // warp-aggregated arrival; the last warp of the group issues this chunk's MMAs
+        // warp-aggregated arrival; the last warp of the group issues the MMAs of both chunks
         if (lane == 0) {
-            const uint32_t old = atom_add_acq_rel_smem(&c.fill[s], 1u);
+            const uint32_t old = atom_add_acq_rel_smem(&c.fill[0], 1u);
             if (old == c.group_warps * (use + 1) - 1) {
                 tc05::fence_after_thread_sync();
-                const uint32_t a_addr = c.ring_addr + s * kSlotBytes;
-                const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
-                const uint64_t b_hi = tc05::make_smem_desc(c.bhi_addr + ch * 256, 2048), b_lo = tc05::make_smem_desc(c.blo_addr + ch * 256, 2048);
                 const uint32_t d = c.tmem_d & 0x0000FFFFu;  // lane 0: the MMA addresses the whole 128-lane tile
-                tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
-                tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
-                tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
-                tc05::mma_commit(&c.slot_free[s]);
-                if (ch == kChunks - 1) tc05::mma_commit(c.d_ready);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int ch = cp * 2 + half;
+                    const uint32_t a_addr = c.ring_addr + half * kSlotBytes;
+                    const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
+                    const uint64_t b_hi = tc05::make_smem_desc(c.bhi_addr + ch * 256, 2048), b_lo = tc05::make_smem_desc(c.blo_addr + ch * 256, 2048);
+                    tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
+                    tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
+                    tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
+                }
+                tc05::mma_commit(&c.slot_free[0]);
+                if (cp == kChunks / 2 - 1) tc05::mma_commit(c.d_ready);
             }
         }
         __syncwarp();
