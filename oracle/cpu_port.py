@@ -160,7 +160,9 @@ def best_thread_count(net_dims=(64, 64), candidates=None, **hyper):
     import os
     ncpu = os.cpu_count() or 8
     if candidates is None:
-        candidates = sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu})
+        # (one thread per logical CPU is pathological on big hosts -- 128 threads measured 400x slower than 16 -- and
+        # would make the calibration itself take a minute, so the sweep stops at 64)
+        candidates = sorted({t for t in (4, 8, 16, 32, 64, min(ncpu, 64)) if t <= ncpu})
     scores = {}
     for t in candidates:
         r = time_cpu_cycles(16384, 32, net_dims, warmup=1, cycles=1, threads=t, **hyper)
