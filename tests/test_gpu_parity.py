@@ -549,3 +549,36 @@ def test_helloworld_agent_rollout_plumbing():
     assert float(buf[2].abs().max()) == 0.0 and buf[4].dtype == th.bool and int((~buf[5]).sum()) == 2
     res = agent.update_net(buf)
     assert len(res) == 3 and np.isfinite(res[:2]).all() and res[2] == 0.0
+
+
+def test_fused_rollout_long_horizon(rollout_impl):
+    """Many steps through the mbarrier / ring phase logic of the persistent kernels: masks and step counters exact for
+    all 300 steps, values against the oracle for the first 48 (before chaotic error growth matters)."""
+    from elegantrl_b200.envs import PendulumVecEnv
+    g = gu.load("rollout_pendulum_n8_h16")
+    n, h, max_step = 130, 300, 37
+    agent = G.agent_from_golden(g, num_envs=n)
+    agent.num_envs, agent.if_vec_env = n, True
+    rng = np.random.default_rng(99)
+    theta0 = rng.uniform(-3, 3, n).astype(np.float32)
+    theta_dot0 = rng.uniform(-1, 1, n).astype(np.float32)
+    cur0 = rng.integers(0, max_step, n).astype(np.int32)
+    eps = rng.standard_normal((h, n, 1)).astype(np.float32)
+    reset_u = rng.random((h, n, 2)).astype(np.float32)
+    env = PendulumVecEnv(num_envs=n, gpu_id=0, max_step=max_step)
+    env.theta, env.theta_dot, env.cur_step = G.cuda(theta0), G.cuda(theta_dot0), G.cuda(cur0)
+    agent._inject_eps, agent._inject_reset_noise = G.cuda(eps), G.cuda(reset_u)
+    states, actions, logprobs, rewards, undones, unmasks = agent.explore_env(env, h)
+    t_idx = np.arange(1, h + 1, dtype=np.int64)[:, None]
+    want_trunc = ((cur0[None, :].astype(np.int64) + t_idx) % max_step) == 0
+    assert np.array_equal(unmasks.cpu().numpy(), ~want_trunc) and bool(undones.all())
+    assert np.array_equal(env.cur_step.cpu().numpy(), (cur0 + h) % max_step)
+    want = po.rollout_pendulum(gu.net_of(g, "actor"), gu.net_of(g, "critic"), theta0, theta_dot0, cur0, 48, eps[:48], reset_u[:48],
+                               float(g["hp.reward_scale"]), max_step)
+    for name, got in zip(("states", "actions", "logprobs", "rewards"), (states, actions, logprobs, rewards)):
+        G.assert_close(got[:48], want[name], RTOL, 2e-5, name)
+    assert th.isfinite(states).all() and th.isfinite(agent._value_cache[1]).all()
+    # every reset row must hold exactly the injected reset noise (bit-exact data path through the kernel)
+    tr = np.argwhere(want_trunc[:-1])
+    got_thd = states[1:, :, 2].cpu().numpy()[tr[:, 0], tr[:, 1]]
+    np.testing.assert_array_equal(got_thd, (reset_u[tr[:, 0], tr[:, 1], 1] * np.float32(2.0) - np.float32(1.0)))
