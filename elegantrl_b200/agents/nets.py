@@ -99,3 +99,26 @@ class CriticPPO(nn.Module, _StateNormMixin):
 
     def forward(self, state: TEN) -> TEN:
         return self.net(self.state_norm(state))
+
+
+class ActorDiscretePPO(ActorPPO):
+    """Categorical policy over ``action_dim`` actions: probs = softmax(MLP(state_norm(s))) -- reference
+    ``elegantrl/agents/AgentPPO.py:393-425``.  Like the reference it inherits ``action_std_log`` (unused: it never
+    receives a gradient, so Adam never touches it) which keeps the state_dict keys interchangeable."""
+
+    def forward(self, state: TEN) -> TEN:  # greedy action index for evaluation
+        return self.net(self.state_norm(state)).argmax(dim=1)
+
+    def get_action(self, state: TEN):  # torch statement of what b200rl_policy_step_discrete does
+        logits = self.net(self.state_norm(state)).log_softmax(dim=-1)
+        race = logits.exp() / th.empty_like(logits).exponential_(1)  # torch.multinomial's one-draw fast path
+        action = race.argmax(dim=-1)
+        return action, logits.gather(1, action[:, None])[:, 0]
+
+    def get_logprob_entropy(self, state: TEN, action: TEN):
+        logits = self.net(self.state_norm(state)).log_softmax(dim=-1)
+        return logits.gather(1, action.long().reshape(-1, 1))[:, 0], -(logits.exp() * logits).sum(1)
+
+    @staticmethod
+    def convert_action_for_env(action: TEN) -> TEN:
+        return action.long()

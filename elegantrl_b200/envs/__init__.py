@@ -1,3 +1,4 @@
 from .pendulum import PendulumVecEnv
+from .cartpole import CartPoleVecEnv
 
-__all__ = ["PendulumVecEnv"]
+__all__ = ["PendulumVecEnv", "CartPoleVecEnv"]

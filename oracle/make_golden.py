@@ -89,6 +89,8 @@ def dump_adam(prefix, optimizer, module, out):
         names.append("action_std_log")
     for p, n in zip(params, names):
         st = optimizer.state[p]
+        if "exp_avg" not in st:  # ActorDiscretePPO.action_std_log never receives a gradient: Adam never creates its state
+            continue
         out[f"{prefix}.m.{n}"] = st["exp_avg"].detach().numpy().copy()
         out[f"{prefix}.v.{n}"] = st["exp_avg_sq"].detach().numpy().copy()
         out[f"{prefix}.step"] = np.float64(float(st["step"]))
@@ -297,7 +299,7 @@ def main():
                  batch_size=16, repeat_times=4)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "elegantrl"):
     main()
 
 
@@ -399,3 +401,136 @@ def main_helloworld():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "helloworld"):
     main_helloworld()
+
+
+# --------------------------------------------------------------------------- discrete PPO
+def make_ref_discrete_agent(state_dim, action_dim, net_dims, num_envs, seed, **hyper):
+    from elegantrl.agents import AgentDiscretePPO as RefAgentDiscretePPO
+    th.manual_seed(seed)
+    env_args = {'env_name': 'golden', 'num_envs': num_envs, 'max_step': 200, 'state_dim': state_dim,
+                'action_dim': action_dim, 'if_discrete': True}
+    args = RefConfig(agent_class=RefAgentDiscretePPO, env_class=None, env_args=env_args)
+    args.net_dims = list(net_dims)
+    for k, v in hyper.items():
+        setattr(args, k, v)
+    return RefAgentDiscretePPO(list(net_dims), state_dim, action_dim, gpu_id=-1, args=args)
+
+
+def replay_exponential(shape, seed):
+    """The Exp(1) draw torch.multinomial's one-sample fast path consumes (q = empty_like(probs).exponential_(1))."""
+    th.manual_seed(seed)
+    return th.empty(shape, dtype=th.float32).exponential_(1)
+
+
+def case_discrete(name, state_dim, action_dim, net_dims, num_envs, horizon_len, seed, num_updates=3, **hyper):
+    """AgentDiscretePPO (AgentPPO.py:252-270) + ActorDiscretePPO (:393-425): nets / sampling with the multinomial noise
+    replayed / update_objectives / update_net on a synthetic buffer whose actions are int32 [H, N] (:103-104)."""
+    out = {}
+    agent = make_ref_discrete_agent(state_dim, action_dim, net_dims, num_envs, seed, **hyper)
+    perturb_nets(agent, seed + 1)
+    with th.no_grad():
+        agent.act.net[-1].weight *= 8.0  # the 0.1-std orthogonal head gives near-uniform probabilities: sharpen them
+    record_hyper(agent, out)
+    out["dims"] = np.array([state_dim, action_dim, num_envs, horizon_len] + list(net_dims), dtype=np.int64)
+    dump_net("actor", agent.act, out)
+    dump_net("critic", agent.cri, out)
+
+    g = th.Generator().manual_seed(seed + 2)
+    state = th.randn((41, state_dim), generator=g) * 1.5
+    action = th.randint(action_dim, (41,), generator=g, dtype=th.int32)
+    with th.no_grad():
+        logprob, entropy = agent.act.get_logprob_entropy(state, action)
+        out["nets.state"], out["nets.action"] = state.numpy(), action.numpy()
+        out["nets.logits"] = agent.act.net(agent.act.state_norm(state)).numpy()
+        out["nets.actor_forward"] = agent.act(state).numpy()
+        out["nets.logprob"], out["nets.entropy"] = logprob.numpy(), entropy.numpy()
+        out["nets.value"] = agent.cri(state).squeeze(1).numpy()
+        # get_action with the sampler's noise replayed
+        expo = replay_exponential((41, action_dim), seed + 6)
+        th.manual_seed(seed + 6)
+        sampled, sampled_logprob = agent.act.get_action(state)
+        probs = th.softmax(agent.act.net(agent.act.state_norm(state)), dim=-1)
+        assert th.equal(sampled, (probs / expo).argmax(dim=-1)), "multinomial noise replay mismatch"
+        out["sample.expo"], out["sample.action"] = expo.numpy(), sampled.numpy()
+        out["sample.logprob"] = sampled_logprob.numpy()
+
+    g = th.Generator().manual_seed(seed + 3)
+    states = th.randn((horizon_len, num_envs, state_dim), generator=g)
+    actions = th.randint(action_dim, (horizon_len, num_envs), generator=g, dtype=th.int32)
+    with th.no_grad():
+        logprobs = agent.act.get_logprob_entropy(states.reshape(-1, state_dim), actions.reshape(-1))[0]
+        logprobs = logprobs.reshape(horizon_len, num_envs) + 0.05 * th.randn((horizon_len, num_envs), generator=g)
+    rewards = th.randn((horizon_len, num_envs), generator=g)
+    terminals = th.rand((horizon_len, num_envs), generator=g) < 0.08
+    truncates = (th.rand((horizon_len, num_envs), generator=g) < 0.08) & ~terminals
+    last_state = th.randn((num_envs, state_dim), generator=g)
+    buf = (states, actions, logprobs, rewards, ~terminals, ~truncates, last_state)
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks", "last_state"), buf):
+        out[f"buf.{k}"] = t.numpy().copy()
+    train_buffer = record_gae(agent, buf, out, "gae")
+    record_update(agent, train_buffer, out, num_updates, seed + 4)
+    record_update_net(agent, buf, out, seed + 5)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def case_discrete_rollout(name, num_envs, horizon_len, max_step, seed, net_dims=(64, 64), **hyper):
+    """Reference _explore_vec_env (:87-129, discrete branch :103-104) + update_net on the torch CartPole vec env: the
+    external-env (per-step) path with integer actions and real terminal flags."""
+    from elegantrl_b200.envs import CartPoleVecEnv
+    out = {}
+    agent = make_ref_discrete_agent(4, 2, net_dims, num_envs, seed, **hyper)
+    perturb_nets(agent, seed + 1)
+    with th.no_grad():
+        agent.act.net[-1].weight *= 8.0
+    record_hyper(agent, out)
+    out["dims"] = np.array([4, 2, num_envs, horizon_len] + list(net_dims), dtype=np.int64)
+    out["max_step"] = np.int64(max_step)
+    dump_net("actor", agent.act, out)
+    dump_net("critic", agent.cri, out)
+
+    env = CartPoleVecEnv(num_envs=num_envs, gpu_id=-1, max_step=max_step, seed=seed)
+    g = th.Generator().manual_seed(seed + 2)
+    reset_noise = th.rand((horizon_len + 1, num_envs, 4), generator=g)
+    env.inject_reset_noise(reset_noise)
+    state, _ = env.reset()
+    env.cur_step[:] = th.randint(0, max_step, (num_envs,), generator=g, dtype=th.int32)
+    out["env.state0"] = env.state.numpy().copy()
+    out["env.cur_step0"] = env.cur_step.numpy().copy()
+    out["env.reset_noise"] = reset_noise[1:].numpy().copy()
+    agent.last_state = state
+
+    th.manual_seed(seed + 3)
+    expo = th.stack([th.empty((num_envs, 2), dtype=th.float32).exponential_(1) for _ in range(horizon_len)])
+    out["expo"] = expo.numpy()
+    th.manual_seed(seed + 3)
+    with th.no_grad():
+        states, actions, logprobs, rewards, undones, unmasks = agent.explore_env(env, horizon_len)
+        probs0 = th.softmax(agent.act.net(agent.act.state_norm(states[0])), dim=-1)
+    assert th.equal(actions[0].long(), (probs0 / expo[0]).argmax(dim=-1)), "multinomial noise replay mismatch"
+    assert (~undones).any() and (~unmasks).any(), "pick a seed with terminals and truncations"
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks"),
+                    (states, actions, logprobs, rewards, undones, unmasks)):
+        out[f"rollout.{k}"] = t.numpy().copy()
+    out["rollout.last_state"] = agent.last_state.numpy().copy()
+    out["rollout.cur_step"] = env.cur_step.numpy().copy()
+    buf = (states, actions, logprobs, rewards, undones, unmasks, agent.last_state.clone())
+    record_gae(agent, buf, out, "gae")
+    record_update_net(agent, buf, out, seed + 5)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main_discrete():
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    # CartPole dims (examples/demo_A2C_PPO_discrete.py), LunarLander-discrete dims (8 states, 4 actions)
+    case_discrete("discrete_s4_a2_64x64", 4, 2, (64, 64), num_envs=12, horizon_len=20, seed=83, batch_size=32, repeat_times=4)
+    case_discrete("discrete_s8_a4_128x64", 8, 4, (128, 64), num_envs=9, horizon_len=14, seed=89, batch_size=24,
+                  repeat_times=4, lambda_entropy=0.05, ratio_clip=0.3, learning_rate=2e-4)
+    case_discrete_rollout("cartpole_n16_h48", num_envs=16, horizon_len=48, max_step=30, seed=97,
+                          batch_size=32, repeat_times=4)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "discrete"):
+    main_discrete()

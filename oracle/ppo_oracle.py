@@ -134,6 +134,39 @@ def logprob_entropy(actor, state, action):
             gaussian_entropy(actor["action_std_log"], state.shape[0], mean.dtype))
 
 
+# ------------------------------------------------------------------------------- discrete (categorical) actor
+def categorical_from_logits(z):
+    """softmax + torch.distributions.Categorical(probs=...) -- reference AgentPPO.py:407-418 (ActorDiscretePPO):
+    ``a_prob = Softmax(net(s))``; Categorical renormalises ``probs / probs.sum(-1)`` and keeps
+    ``logits = log(clamp(probs, eps, 1 - eps))`` (torch/distributions/utils.py probs_to_logits).  Returns (probs, logits)."""
+    dt = z.dtype
+    e = np.exp(z - z.max(axis=1, keepdims=True))
+    p = (e / e.sum(axis=1, keepdims=True)).astype(dt)
+    p = (p / p.sum(axis=1, keepdims=True)).astype(dt)
+    eps = np.finfo(dt).eps
+    return p, np.log(np.clip(p, eps, 1 - eps)).astype(dt)
+
+
+def categorical_sample(probs, expo):
+    """Categorical.sample() = torch.multinomial(probs, 1): ATen's one-draw fast path is the exponential race
+    ``argmax(probs / q)``, q ~ Exp(1) (aten/src/ATen/native/Sampling / multinomial "fast path").  ``expo`` [B, A] injects q."""
+    return np.argmax(probs / expo.astype(probs.dtype), axis=1).astype(np.int64)
+
+
+def sample_action_discrete(actor, state, expo):
+    """ActorDiscretePPO.get_action with the Exp(1) noise injected -- reference AgentPPO.py:407-413."""
+    p, logits = categorical_from_logits(actor_mean(actor, state))
+    action = categorical_sample(p, expo)
+    return action, np.take_along_axis(logits, action[:, None], axis=1)[:, 0]
+
+
+def logprob_entropy_discrete(actor, state, action):
+    """ActorDiscretePPO.get_logprob_entropy -- reference AgentPPO.py:415-421 (entropy = -sum p * logits)."""
+    p, logits = categorical_from_logits(actor_mean(actor, state))
+    logprob = np.take_along_axis(logits, action.astype(np.int64)[:, None], axis=1)[:, 0]
+    return logprob, (-(p * logits).sum(axis=1)).astype(p.dtype)
+
+
 # ------------------------------------------------------------------------------------------------ env
 def pendulum_observe(theta, theta_dot):
     return np.stack((np.cos(theta), np.sin(theta), theta_dot), axis=1).astype(theta.dtype)
@@ -194,6 +227,57 @@ def rollout_pendulum(actor, critic, theta, theta_dot, cur_step, horizon_len, eps
                undones=~terminals, unmasks=~truncates, values=values,
                last_state=pendulum_observe(theta, theta_dot), theta=theta, theta_dot=theta_dot, cur_step=cur_step)
     return out
+
+
+def cartpole_step(state, cur_step, action, reset_u, max_step=500):
+    """One step of ``elegantrl_b200.envs.CartPoleVecEnv.step`` (classic cart-pole, Euler, tau 0.02; terminal beyond
+    +-2.4 m / +-12 deg, truncation at max_step, auto-reset to U(-0.05, 0.05) -- vec-env contract of reference
+    elegantrl/train/config.py:243-247).  action [N] int.  Returns (state, cur_step, reward, terminal, truncate)."""
+    dt = state.dtype
+    f = dt.type
+    x, x_dot, theta, theta_dot = (state[:, i] for i in range(4))
+    force = np.where(action > 0, f(10.0), f(-10.0)).astype(dt)
+    cos_t, sin_t = np.cos(theta), np.sin(theta)
+    temp = (force + f(0.1 * 0.5) * (theta_dot * theta_dot) * sin_t) / f(1.1)
+    theta_acc = (f(9.8) * sin_t - cos_t * temp) / (f(0.5) * (f(4.0 / 3.0) - f(0.1) * (cos_t * cos_t) / f(1.1)))
+    x_acc = temp - f(0.1 * 0.5) * theta_acc * cos_t / f(1.1)
+    x = x + f(0.02) * x_dot
+    x_dot = x_dot + f(0.02) * x_acc
+    theta = theta + f(0.02) * theta_dot
+    theta_dot = theta_dot + f(0.02) * theta_acc
+    new_state = np.stack((x, x_dot, theta, theta_dot), axis=1).astype(dt)
+    cur_step = cur_step + 1
+    terminal = (np.abs(x) > f(2.4)) | (np.abs(theta) > f(12 * 2 * math.pi / 360))
+    truncate = (cur_step >= max_step) & ~terminal
+    done = terminal | truncate
+    fresh = (reset_u.astype(dt) * f(0.1) - f(0.05)).astype(dt)
+    new_state = np.where(done[:, None], fresh, new_state).astype(dt)
+    cur_step = np.where(done, 0, cur_step).astype(np.int32)
+    return new_state, cur_step, np.ones(state.shape[0], dt), terminal, truncate
+
+
+def rollout_cartpole(actor, critic, state, cur_step, horizon_len, expo, reset_u, reward_scale=1.0, max_step=500):
+    """AgentPPO._explore_vec_env, discrete branch (actions int32 [H, N]) -- reference AgentPPO.py:87-129 with
+    ActorDiscretePPO.get_action (:407-413) and convert_action_for_env = .long() (:423-425)."""
+    dt = state.dtype
+    n = state.shape[0]
+    states = np.zeros((horizon_len, n, 4), dt)
+    actions = np.zeros((horizon_len, n), np.int32)
+    logprobs = np.zeros((horizon_len, n), dt)
+    rewards = np.zeros((horizon_len, n), dt)
+    terminals = np.zeros((horizon_len, n), bool)
+    truncates = np.zeros((horizon_len, n), bool)
+    values = np.zeros((horizon_len, n), dt)
+    for t in range(horizon_len):
+        action, logprob = sample_action_discrete(actor, state, expo[t])
+        states[t], actions[t], logprobs[t] = state, action, logprob
+        if critic is not None:
+            values[t] = critic_value(critic, state)
+        state, cur_step, reward, terminal, truncate = cartpole_step(state, cur_step, action, reset_u[t], max_step)
+        rewards[t], terminals[t], truncates[t] = reward, terminal, truncate
+    rewards = (rewards * dt.type(reward_scale)).astype(dt)
+    return dict(states=states, actions=actions, logprobs=logprobs, rewards=rewards, undones=~terminals,
+                unmasks=~truncates, values=values, last_state=state, cur_step=cur_step)
 
 
 # ------------------------------------------------------------------------------------------------ GAE
@@ -339,12 +423,19 @@ def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
     # actor: ratio, "clip" as a constant factor, entropy sign as in the reference   (:193-204)
     xa = state_norm(actor, state)
     mean, acts_a, pre_a = mlp_forward(actor, xa, keep=True)
-    std_log = actor["action_std_log"].astype(dt)
-    std = np.exp(std_log)
-    var = std * std
-    diff = action - mean
-    new_logprob = (-(diff ** 2) / (2 * var) - np.log(std) - dt.type(LOG_SQRT_2PI)).sum(axis=1)
-    entropy = gaussian_entropy(std_log, state.shape[0], dt)
+    discrete = hp.get("discrete", False)
+    if discrete:  # ActorDiscretePPO.get_logprob_entropy (:415-421): `mean` holds the logits, `action` the int indices
+        probs, logits = categorical_from_logits(mean)
+        act_idx = np.asarray(action).astype(np.int64).reshape(-1)
+        new_logprob = np.take_along_axis(logits, act_idx[:, None], axis=1)[:, 0]
+        entropy = (-(probs * logits).sum(axis=1)).astype(dt)
+    else:
+        std_log = actor["action_std_log"].astype(dt)
+        std = np.exp(std_log)
+        var = std * std
+        diff = action - mean
+        new_logprob = (-(diff ** 2) / (2 * var) - np.log(std) - dt.type(LOG_SQRT_2PI)).sum(axis=1)
+        entropy = gaussian_entropy(std_log, state.shape[0], dt)
     ratio = np.exp(new_logprob - batch["logprob"])
     adv = batch["advantage"]
     mask_a = unmask if hp.get("mask_actor", True) else np.ones_like(unmask)  # helloworld does not mask the actor terms
@@ -364,11 +455,21 @@ def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
     lam_ent = dt.type(hp["lambda_entropy"])
     # loss = -(obj_surrogate - obj_entropy * lambda_entropy)
     g_logp = (-(d_ratio * ratio * mask_a) / bsz).astype(dt)                 # d loss / d new_logprob
-    d_mean = (g_logp[:, None] * diff / var).astype(dt)                      # d logp / d mu = (a - mu) / var
-    d_std_log = (g_logp[:, None] * (diff * diff / var - dt.type(1.0))).sum(axis=0, keepdims=True) \
-        + ent_sign * lam_ent * mask_a.mean(dtype=dt)                        # d entropy / d std_log = 1
-    dWa, dba, _ = mlp_backward(actor, acts_a, pre_a, d_mean)
-    ga = [g for pair in zip(dWa, dba) for g in pair] + [d_std_log.astype(dt)]
+    if discrete:
+        # d logp[a] / d z = onehot(a) - p;  d entropy / d z_j = -p_j (log p_j + entropy)   (log-softmax algebra; the
+        # eps clamp of probs_to_logits is inactive unless a probability underflows 1.2e-7)
+        onehot = np.zeros_like(probs)
+        onehot[np.arange(probs.shape[0]), act_idx] = 1
+        g_ent = (ent_sign * lam_ent * mask_a / bsz).astype(dt)              # d loss / d entropy_b
+        d_mean = (g_logp[:, None] * (onehot - probs) - g_ent[:, None] * probs * (logits + entropy[:, None])).astype(dt)
+        dWa, dba, _ = mlp_backward(actor, acts_a, pre_a, d_mean)
+        ga = [g for pair in zip(dWa, dba) for g in pair]
+    else:
+        d_mean = (g_logp[:, None] * diff / var).astype(dt)                  # d logp / d mu = (a - mu) / var
+        d_std_log = (g_logp[:, None] * (diff * diff / var - dt.type(1.0))).sum(axis=0, keepdims=True) \
+            + ent_sign * lam_ent * mask_a.mean(dtype=dt)                    # d entropy / d std_log = 1
+        dWa, dba, _ = mlp_backward(actor, acts_a, pre_a, d_mean)
+        ga = [g for pair in zip(dWa, dba) for g in pair] + [d_std_log.astype(dt)]
     ga, norm_a = clip_grads(ga, hp["clip_grad_norm"])
 
     # Adam, critic first (:191) then actor (:204); the nets are disjoint so the order is immaterial
@@ -376,9 +477,9 @@ def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
     mc = [p for pair in zip(opt_c["m_W"], opt_c["m_b"]) for p in pair]
     vc = [p for pair in zip(opt_c["v_W"], opt_c["v_b"]) for p in pair]
     opt_c["step"] = adam_step(pc, gc, mc, vc, opt_c["step"], hp["learning_rate"])
-    pa = [p for pair in zip(actor["W"], actor["b"]) for p in pair] + [actor["action_std_log"]]
-    ma = [p for pair in zip(opt_a["m_W"], opt_a["m_b"]) for p in pair] + [opt_a["m_std"]]
-    va = [p for pair in zip(opt_a["v_W"], opt_a["v_b"]) for p in pair] + [opt_a["v_std"]]
+    pa = [p for pair in zip(actor["W"], actor["b"]) for p in pair] + ([] if discrete else [actor["action_std_log"]])
+    ma = [p for pair in zip(opt_a["m_W"], opt_a["m_b"]) for p in pair] + ([] if discrete else [opt_a["m_std"]])
+    va = [p for pair in zip(opt_a["v_W"], opt_a["v_b"]) for p in pair] + ([] if discrete else [opt_a["v_std"]])
     opt_a["step"] = adam_step(pa, ga, ma, va, opt_a["step"], hp["learning_rate"])
     return (float(obj_critic), float(obj_surrogate), float(obj_entropy)), \
         dict(critic=gc, actor=ga, norm_critic=float(norm_c), norm_actor=float(norm_a))

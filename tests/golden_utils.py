@@ -60,3 +60,14 @@ def helloworld_hyper_of(g):
     return dict(gamma=float(g["hp.gamma"]), lambda_gae_adv=float(g["hp.lambda_gae_adv"]), ratio_clip=float(g["hp.ratio_clip"]),
                 lambda_entropy=float(g["hp.lambda_entropy"]), learning_rate=float(g["hp.learning_rate"]),
                 batch_size=int(g["hp.batch_size"]), repeat_times=float(g["hp.repeat_times"]))
+
+
+DISCRETE_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "discrete_*.npz")))
+CARTPOLE_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "cartpole_*.npz")))
+
+
+def discrete_net_of(g, prefix, dtype=np.float32):
+    """ActorDiscretePPO: the inherited action_std_log is dead weight (reference AgentPPO.py:393-397), drop it."""
+    net = net_of(g, prefix, dtype)
+    net.pop("action_std_log", None)
+    return net
