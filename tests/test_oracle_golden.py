@@ -141,3 +141,77 @@ def test_helloworld_update_net(case):
     for prefix, net in (("actor", actor), ("critic", critic)):
         for mine, ref in zip(gu.flat_params(net), gu.flat_params(gu.plain_net_of(g, f"update_net.after.{prefix}"))):
             np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------- discrete PPO
+@pytest.mark.parametrize("case", gu.DISCRETE_CASES)
+def test_discrete_nets_and_sampling(case):
+    """ActorDiscretePPO (reference AgentPPO.py:393-425): logits, greedy action, log-prob / entropy of Categorical, and
+    get_action with torch.multinomial's Exp(1) noise replayed -- sampled indices bit-exact."""
+    g = gu.load(case)
+    actor, critic = gu.discrete_net_of(g, "actor"), gu.net_of(g, "critic")
+    state = g["nets.state"]
+    np.testing.assert_allclose(po.actor_mean(actor, state), g["nets.logits"], **F32)
+    assert np.array_equal(np.argmax(po.actor_mean(actor, state), axis=1), g["nets.actor_forward"])
+    logprob, entropy = po.logprob_entropy_discrete(actor, state, g["nets.action"])
+    np.testing.assert_allclose(logprob, g["nets.logprob"], **F32)
+    np.testing.assert_allclose(entropy, g["nets.entropy"], **F32)
+    np.testing.assert_allclose(po.critic_value(critic, state), g["nets.value"], **F32)
+    action, sampled_logprob = po.sample_action_discrete(actor, state, g["sample.expo"])
+    assert np.array_equal(action, g["sample.action"])
+    np.testing.assert_allclose(sampled_logprob, g["sample.logprob"], **F32)
+
+
+@pytest.mark.parametrize("case", gu.DISCRETE_CASES)
+def test_discrete_update_objectives(case):
+    g = gu.load(case)
+    hp = dict(gu.hyper_of(g), discrete=True)
+    actor, critic = gu.discrete_net_of(g, "actor"), gu.net_of(g, "critic")
+    opt_a, opt_c = po.new_adam_state(actor, False), po.new_adam_state(critic, False)
+    buffer = dict(states=g["buf.states"], actions=g["buf.actions"], unmasks=g["buf.unmasks"],
+                  logprobs=g["buf.logprobs"], advantages=g["gae.adv_norm"], reward_sums=g["gae.reward_sums"])
+    for u, ids in enumerate(g["update.ids"]):
+        scalars, _ = po.ppo_minibatch(actor, critic, opt_a, opt_c, po.gather_minibatch(buffer, ids), hp)
+        np.testing.assert_allclose(scalars, g["update.scalars"][u], rtol=1e-4, atol=1e-6)
+    for prefix, net, opt in (("actor", actor, opt_a), ("critic", critic, opt_c)):
+        for mine, ref in zip(gu.flat_params(net), gu.flat_params(gu.discrete_net_of(g, f"update.after.{prefix}"))):
+            np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=2e-6)
+        for i in range(len(net["W"])):
+            np.testing.assert_allclose(opt["m_W"][i], g[f"update.after.{prefix}_adam.m.W{i}"], rtol=1e-3, atol=1e-7)
+    # the inherited action_std_log never moves (no gradient reaches it)
+    assert np.array_equal(g["update.after.actor.action_std_log"], g["actor.action_std_log"])
+
+
+@pytest.mark.parametrize("case", gu.DISCRETE_CASES + gu.CARTPOLE_CASES)
+def test_discrete_update_net(case):
+    g = gu.load(case)
+    hp = dict(gu.hyper_of(g), discrete=True)
+    actor, critic = gu.discrete_net_of(g, "actor"), gu.net_of(g, "critic")
+    opt_a, opt_c = po.new_adam_state(actor, False), po.new_adam_state(critic, False)
+    src = "buf" if "buf.states" in g else "rollout"
+    rollout = {k: g[f"{src}.{k}"].copy() for k in ("states", "actions", "logprobs", "rewards", "undones", "unmasks")}
+    result, _ = po.update_net(actor, critic, opt_a, opt_c, rollout, g[f"{src}.last_state"], g["update_net.ids"], hp)
+    np.testing.assert_allclose(result, g["update_net.result"], rtol=1e-4, atol=1e-6)
+    for prefix, net in (("actor", actor), ("critic", critic)):
+        for mine, ref in zip(gu.flat_params(net), gu.flat_params(gu.discrete_net_of(g, f"update_net.after.{prefix}"))):
+            np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("case", gu.CARTPOLE_CASES)
+def test_discrete_rollout_cartpole(case):
+    """Reference _explore_vec_env (discrete branch) on the torch CartPole vec env: integer actions and both masks
+    bit-exact (real terminals AND truncations occur), floats to 1e-4."""
+    g = gu.load(case)
+    hp = gu.hyper_of(g)
+    actor, critic = gu.discrete_net_of(g, "actor"), gu.net_of(g, "critic")
+    horizon_len = g["rollout.states"].shape[0]
+    out = po.rollout_cartpole(actor, critic, g["env.state0"], g["env.cur_step0"], horizon_len, g["expo"],
+                              g["env.reset_noise"], hp["reward_scale"], int(g["max_step"]))
+    assert np.array_equal(out["actions"], g["rollout.actions"]) and out["actions"].dtype == g["rollout.actions"].dtype
+    assert np.array_equal(out["undones"], g["rollout.undones"]) and np.array_equal(out["unmasks"], g["rollout.unmasks"])
+    assert not g["rollout.undones"].all() and not g["rollout.unmasks"].all()
+    assert np.array_equal(out["cur_step"], g["rollout.cur_step"])
+    for k in ("states", "logprobs", "rewards"):
+        np.testing.assert_allclose(out[k], g[f"rollout.{k}"], rtol=1e-4, atol=1e-5, err_msg=k)
+    np.testing.assert_allclose(out["last_state"], g["rollout.last_state"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["values"], g["gae.values"], rtol=1e-4, atol=1e-5)
