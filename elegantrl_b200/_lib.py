@@ -43,7 +43,7 @@ PPO_HELLOWORLD = PPO_SMOOTH_L1 | PPO_MIN_CLIP | PPO_ENTROPY_BONUS | PPO_ACTOR_UN
 class TrainBuffer(C.Structure):
     _fields_ = [("states", C.c_void_p), ("actions", C.c_void_p), ("unmasks", C.c_void_p), ("logprobs", C.c_void_p),
                 ("advantages", C.c_void_p), ("reward_sums", C.c_void_p), ("adv_stats", C.c_void_p),
-                ("horizon_len", C.c_int32), ("num_envs", C.c_int32)]
+                ("horizon_len", C.c_int32), ("num_envs", C.c_int32), ("discrete_actions", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RolloutArgs(C.Structure):
@@ -69,6 +69,9 @@ SIGNATURES = {
     "b200rl_mlp_forward": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200rl_policy_step": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
                                      C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200rl_policy_step_discrete": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
+                                              C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200rl_set_policy_step_base": (None, [C.c_void_p]),
     "b200rl_rollout_pendulum": (C.c_int, [C.POINTER(RolloutArgs), C.c_void_p]),
     "b200rl_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                              C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

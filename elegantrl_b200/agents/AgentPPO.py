@@ -26,7 +26,7 @@ import torch as th
 from torch import nn
 
 from .. import _lib
-from .nets import ActorPPO, CriticPPO
+from .nets import ActorDiscretePPO, ActorPPO, CriticPPO
 
 TEN = th.Tensor
 
@@ -35,18 +35,25 @@ def _linears(module: nn.Module):
     return [m for m in module.net if isinstance(m, nn.Linear)]
 
 
+def _has_std(module: nn.Module) -> bool:
+    """Gaussian actors train ``action_std_log``; the categorical actor only inherits it as dead weight (reference
+    AgentPPO.py:393-397) and the critic has none."""
+    return hasattr(module, "action_std_log") and not isinstance(module, ActorDiscretePPO)
+
+
 def _trainable(module: nn.Module):
     """Trainable tensors in the engine's flat order: W0, b0, W1, b1, ..., action_std_log."""
     out = []
     for layer in _linears(module):
         out += [layer.weight, layer.bias]
-    if hasattr(module, "action_std_log"):
+    if _has_std(module):
         out.append(module.action_std_log)
     return out
 
 
 class AgentPPO:
     """PPO + GAE with the reference's arithmetic (incl. its quirks), B200-native engine."""
+    _categorical = False  # AgentDiscretePPO flips it: Categorical policy, int32 actions [H, N]
 
     def __init__(self, net_dims, state_dim: int, action_dim: int, gpu_id: int = 0, args=None):
         if args is None:
@@ -73,12 +80,14 @@ class AgentPPO:
         self.last_state: Optional[TEN] = None
         self.device = th.device(f"cuda:{gpu_id}" if (th.cuda.is_available() and gpu_id >= 0) else "cpu")
         self.if_vec_env = self.num_envs > 1
-        assert not self.if_discrete, "this engine carries the continuous-action PPO path"
+        assert bool(self.if_discrete) == self._categorical, \
+            "AgentPPO is the continuous-action agent, AgentDiscretePPO the discrete one (env_args['if_discrete'])"
 
         # ---- fields of AgentPPO.__init__ (reference AgentPPO.py:18-32)
         activation = getattr(args, "activation", "gelu")
         state_norm = getattr(args, "use_state_norm", True)
-        self.act = ActorPPO(self.net_dims, self.state_dim, self.action_dim, activation, state_norm).to(self.device)
+        actor_class = ActorDiscretePPO if self._categorical else ActorPPO
+        self.act = actor_class(self.net_dims, self.state_dim, self.action_dim, activation, state_norm).to(self.device)
         self.cri = CriticPPO(self.net_dims, self.state_dim, self.action_dim, activation, state_norm).to(self.device)
         self.act_target = self.cri_target = None
         self.act_optimizer = th.optim.Adam(self.act.parameters(), self.learning_rate)
@@ -99,6 +108,8 @@ class AgentPPO:
         self._dist_group = None      # set by enable_data_parallel()
         self._rank, self._world = 0, 1
         self.last_update_info = {}
+        self.cuda_graph_rollout = bool(getattr(args, "cuda_graph_rollout", False))  # external envs: see _explore_vec_env_graphed
+        self._rollout_graphs = {}
         self._ppo_flags = 0          # b200rl_ppo_hyper.flags: 0 = the reference's elegantrl arithmetic
         self._full_std = False       # advantage std over the whole buffer instead of the [::4, ::4] lattice
 
@@ -129,7 +140,7 @@ class AgentPPO:
         if getattr(module, "state_avg", None) is not None:
             net.state_avg = self._check(module.state_avg.data, "state_avg").data_ptr()
             net.state_std = self._check(module.state_std.data, "state_std").data_ptr()
-        if hasattr(module, "action_std_log"):
+        if _has_std(module):
             net.action_std_log = self._check(module.action_std_log.data, "action_std_log").data_ptr()
         return net
 
@@ -148,7 +159,7 @@ class AgentPPO:
                 st = self._adam_state(optimizer, p)
                 avg[i], sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
                 step = float(st["step"]) if step is None else step
-        if hasattr(module, "action_std_log"):
+        if _has_std(module):
             st = self._adam_state(optimizer, module.action_std_log)
             adam.exp_avg_std, adam.exp_avg_sq_std = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
         adam.step = int(step or 0)
@@ -195,6 +206,8 @@ class AgentPPO:
         if getattr(env, "env_kind", None) == "pendulum" and self._fused_rollout_ok(env):
             return self._explore_fused_pendulum(env, horizon_len)
         if self.if_vec_env:
+            if self.cuda_graph_rollout and getattr(env, "device", None) == self.device:
+                return self._explore_vec_env_graphed(env, horizon_len)
             return self._explore_vec_env(env, horizon_len)
         return self._explore_one_env(env, horizon_len)
 
@@ -241,10 +254,20 @@ class AgentPPO:
         return action, logprob
 
     def _policy_step(self, state: TEN, eps: Optional[TEN] = None):
-        """One engine exploration step: (action [rows, A] pre-tanh, logprob [rows], env_action = tanh(action))."""
+        """One engine exploration step: (action [rows, A] pre-tanh, logprob [rows], env_action = tanh(action));
+        categorical policy: (action int32 [rows], logprob [rows], env_action = action.long())."""
         lib = self._require_engine()
         state = self._check(state.to(self.device, th.float32).contiguous(), "state")
         rows = state.shape[0]
+        if self._categorical:
+            action = th.empty((rows,), dtype=th.int32, device=self.device)
+            logprob = th.empty((rows,), dtype=th.float32, device=self.device)
+            act_desc = self._net_desc(self.act)
+            _lib.check(lib.b200rl_policy_step_discrete(C.byref(act_desc), None, _lib.ptr(state), rows, _lib.ptr(eps), self.seed,
+                                                       self._policy_steps, self._rank * rows, _lib.ptr(action),
+                                                       _lib.ptr(logprob), None, self._stream()), "policy_step_discrete")
+            self._policy_steps += 1
+            return action, logprob, action.long()
         action = th.empty((rows, self.action_dim), dtype=th.float32, device=self.device)
         env_action = th.empty_like(action)
         logprob = th.empty((rows,), dtype=th.float32, device=self.device)
@@ -259,14 +282,15 @@ class AgentPPO:
         """External tensor vec env: engine policy step + the env's own step(), per time step."""
         n, h, dev = self.num_envs, int(horizon_len), self.device
         states = th.empty((h, n, self.state_dim), dtype=th.float32, device=dev)
-        actions = th.empty((h, n, self.action_dim), dtype=th.float32, device=dev)
+        actions = self._new_actions(h, n)
         logprobs = th.empty((h, n), dtype=th.float32, device=dev)
         rewards = th.empty((h, n), dtype=th.float32, device=dev)
         terminals = th.empty((h, n), dtype=th.bool, device=dev)
         truncates = th.empty((h, n), dtype=th.bool, device=dev)
         state = self.last_state.to(dev)
+        noise = getattr(self, "_inject_eps", None)  # parity tests: [H, N, A] N(0,1) (Gaussian) / Exp(1) (categorical)
         for t in range(h):
-            action, logprob, env_action = self._policy_step(state)
+            action, logprob, env_action = self._policy_step(state, None if noise is None else noise[t].contiguous())
             states[t], actions[t], logprobs[t] = state, action, logprob
             state, reward, terminal, truncate, _ = env.step(env_action)
             state = state.to(dev)
@@ -276,11 +300,76 @@ class AgentPPO:
         self._value_cache = None
         return states, actions, logprobs, rewards, th.logical_not(terminals), th.logical_not(truncates)
 
+    def _explore_vec_env_graphed(self, env, horizon_len: int):
+        """``_explore_vec_env`` with the whole H-step loop -- policy-step kernels, the env's own torch ops, the stores --
+        captured ONCE in a CUDA graph and replayed every cycle (opt-in: ``agent.cuda_graph_rollout = True``).  An eager
+        torch vec env costs dozens of launches per step; the replay removes the launch and Python overhead.
+        Requirements on the env: tensors on this device, ``step`` free of host synchronisation (no ``.item()``, no
+        data-dependent shapes), state kept in tensor attributes of the env object (attributes that ``step`` rebinds are
+        copied back into their original storage at the end of the graph), randomness from ``torch.Generator`` attributes
+        (registered with the graph so that replays draw fresh numbers).  The policy's Philox step counter lives in device
+        memory and is advanced inside the graph.  The returned tensors are STATIC: the next call overwrites them (the
+        reference's loops consume a buffer before they roll out again, run.py:104-130)."""
+        lib = _lib.load()
+        n, h, dev = self.num_envs, int(horizon_len), self.device
+        key = (id(env), h, n)
+        rec = self._rollout_graphs.get(key)
+        if rec is None:
+            rec = dict(state=self.last_state.to(dev, th.float32).clone(), step_base=th.zeros(1, dtype=th.int64, device=dev),
+                       states=th.empty((h, n, self.state_dim), dtype=th.float32, device=dev), actions=self._new_actions(h, n),
+                       logprobs=th.empty((h, n), dtype=th.float32, device=dev), rewards=th.empty((h, n), dtype=th.float32, device=dev),
+                       terminals=th.empty((h, n), dtype=th.bool, device=dev), truncates=th.empty((h, n), dtype=th.bool, device=dev),
+                       undones=th.empty((h, n), dtype=th.bool, device=dev), unmasks=th.empty((h, n), dtype=th.bool, device=dev))
+            graph = th.cuda.CUDAGraph()
+            for value in vars(env).values():
+                if isinstance(value, th.Generator) and value.device.type == "cuda":
+                    graph.register_generator_state(value)
+            before = {k: v for k, v in vars(env).items() if th.is_tensor(v) and v.is_cuda}
+            lib.b200rl_set_policy_step_base(rec["step_base"].data_ptr())
+            try:
+                with th.cuda.graph(graph):
+                    state = rec["state"]
+                    for t in range(h):
+                        action, logprob, env_action = self._policy_step(state)
+                        rec["states"][t].copy_(state)
+                        rec["actions"][t].copy_(action)
+                        rec["logprobs"][t].copy_(logprob)
+                        state, reward, terminal, truncate, _ = env.step(env_action)
+                        rec["rewards"][t].copy_(reward)
+                        rec["terminals"][t].copy_(terminal)
+                        rec["truncates"][t].copy_(truncate)
+                    rec["rewards"].mul_(self.reward_scale)
+                    th.logical_not(rec["terminals"], out=rec["undones"])
+                    th.logical_not(rec["truncates"], out=rec["unmasks"])
+                    rec["state"].copy_(state)
+                    for name, old in before.items():  # state the env rebound to fresh tensors goes back to its storage
+                        new = getattr(env, name)
+                        if new is not old and th.is_tensor(new) and new.shape == old.shape and new.dtype == old.dtype:
+                            old.copy_(new)
+                            setattr(env, name, old)
+                    rec["step_base"].add_(h)
+            finally:
+                lib.b200rl_set_policy_step_base(None)
+            rec["graph"] = graph
+            self._rollout_graphs[key] = rec
+        elif self.last_state is not rec["state"]:
+            rec["state"].copy_(self.last_state)  # the caller reset the env / replaced the observation
+        rec["graph"].replay()
+        self.last_state = rec["state"]
+        self._value_cache = None
+        return rec["states"], rec["actions"], rec["logprobs"], rec["rewards"], rec["undones"], rec["unmasks"]
+
+    def _new_actions(self, h: int, n: int) -> TEN:
+        """fp32 [H, N, A] raw actions, or int32 [H, N] indices for the discrete agent (reference AgentPPO.py:102-104)."""
+        if self._categorical:
+            return th.empty((h, n), dtype=th.int32, device=self.device)
+        return th.empty((h, n, self.action_dim), dtype=th.float32, device=self.device)
+
     def _explore_one_env(self, env, horizon_len: int):
         """Single gym-style env with numpy I/O (reference AgentPPO.py:34-85); outputs shaped [H, 1, ...]."""
         h, dev = int(horizon_len), self.device
         states = th.empty((h, 1, self.state_dim), dtype=th.float32, device=dev)
-        actions = th.empty((h, 1, self.action_dim), dtype=th.float32, device=dev)
+        actions = self._new_actions(h, 1)
         logprobs = th.empty((h, 1), dtype=th.float32, device=dev)
         rewards = th.zeros((h, 1), dtype=th.float32)
         terminals = th.zeros((h, 1), dtype=th.bool)
@@ -342,7 +431,11 @@ class AgentPPO:
         h, n = states.shape[0], states.shape[1]
         dev = self.device
         states = self._check(states, "states")
-        actions = self._check(actions.reshape(h, n, self.action_dim), "actions")
+        if self._categorical:
+            actions = actions.reshape(h, n)
+            assert actions.dtype == th.int32 and actions.is_contiguous() and actions.is_cuda, "actions: int32 indices [H, N]"
+        else:
+            actions = self._check(actions.reshape(h, n, self.action_dim), "actions")
 
         # values: reuse what the fused rollout already computed with this very critic
         cache = self._value_cache
@@ -370,7 +463,8 @@ class AgentPPO:
         workspace = self._get_workspace(act_desc, cri_desc)
         tb = _lib.TrainBuffer(states=_lib.ptr(states), actions=_lib.ptr(actions), unmasks=_lib.ptr(unmasks),
                               logprobs=_lib.ptr(self._check(logprobs, "logprobs")), advantages=_lib.ptr(advantages),
-                              reward_sums=_lib.ptr(reward_sums), adv_stats=_lib.ptr(stats), horizon_len=h, num_envs=n)
+                              reward_sums=_lib.ptr(reward_sums), adv_stats=_lib.ptr(stats), horizon_len=h, num_envs=n,
+                              discrete_actions=int(self._categorical))
         hp = _lib.PPOHyper(ratio_clip=float(self.ratio_clip), lambda_entropy=float(self.lambda_entropy),
                            clip_grad_norm=float(self.clip_grad_norm or 0.0), flags=int(self._ppo_flags))
         out = th.empty(3, dtype=th.float32, device=dev)
@@ -415,7 +509,8 @@ class AgentPPO:
                 j = th.arange(local_batch, device=self.device).view(1, 1, -1)
                 self._packed_ids = (r + u + j).reshape(update_times, -1).contiguous()
                 self._packed_ids_key = key
-            packed = _lib.TrainBuffer(states=_lib.ptr(recv), horizon_len=0, num_envs=recv.shape[0])
+            packed = _lib.TrainBuffer(states=_lib.ptr(recv), horizon_len=0, num_envs=recv.shape[0],
+                                      discrete_actions=int(self._categorical))
             _lib.check(lib.b200rl_ppo_update(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam),
                                              C.byref(packed), C.byref(hp), self.batch_size, update_times,
                                              _lib.ptr(self._packed_ids), self.seed, self._update_draws, _lib.ptr(out),
@@ -471,3 +566,18 @@ class AgentPPO:
                                               for k, v in loaded.state[p_old].items()}
                 setattr(self, opt_name, fresh)
         self._value_cache = None
+
+
+class AgentDiscretePPO(AgentPPO):
+    """Drop-in for the reference's ``AgentDiscretePPO`` (``elegantrl/agents/AgentPPO.py:252-270``): the same cycle with a
+    Categorical policy (``ActorDiscretePPO`` :393-425).  ``explore_env`` returns ``actions`` as int32 ``[H, N]`` (:103-104)
+    and hands ``action.long()`` to ``env.step`` (:423-425); ``lambda_entropy`` defaults to 0.01 (:263)."""
+    _categorical = True
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int, gpu_id: int = 0, args=None):
+        if args is None:
+            from ..config import Config
+            args = Config()
+            args.if_discrete = True
+        super().__init__(net_dims, state_dim, action_dim, gpu_id, args)
+        self.lambda_entropy = getattr(args, "lambda_entropy", 0.01)

@@ -1,5 +1,5 @@
-from .AgentPPO import AgentPPO
-from .nets import ActorPPO, CriticPPO
+from .AgentPPO import AgentDiscretePPO, AgentPPO
+from .nets import ActorDiscretePPO, ActorPPO, CriticPPO
 from . import helloworld
 
-__all__ = ["AgentPPO", "ActorPPO", "CriticPPO", "helloworld"]
+__all__ = ["AgentPPO", "AgentDiscretePPO", "ActorPPO", "ActorDiscretePPO", "CriticPPO", "helloworld"]

@@ -118,6 +118,13 @@ DEV RolloutNoise rollout_noise(uint64_t seed, uint64_t env, uint64_t step, uint3
     n.uniform = make_float2(u32_to_unit(r.z), u32_to_unit(r.w));
     return n;
 }
+// raw Philox words of the rollout stream (categorical sampling draws its Exp(1) noise from them, 4 actions per call;
+// chunk numbers >= 0x800000 keep it apart from the Gaussian path's chunks)
+DEV uint4 rollout_bits(uint64_t seed, uint64_t env, uint64_t step, uint32_t chunk) {
+    uint4 ctr = make_uint4((uint32_t)env, (uint32_t)(env >> 32) ^ ((chunk | 0x800000u) << 8), (uint32_t)step,
+                           (uint32_t)(step >> 32) ^ kStreamRollout);
+    return philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
 // uniform integer in [0, range) for minibatch sampling (replaces th.randint of reference AgentPPO.py:178)
 DEV int64_t sample_index(uint64_t seed, uint64_t draw, uint32_t slot, uint64_t range) {
     uint4 ctr = make_uint4(slot, 0u, (uint32_t)draw, (uint32_t)(draw >> 32) ^ (kStreamIds << 16));

@@ -8,16 +8,20 @@ namespace {
 
 constexpr int kFwdThreads = 256;
 
+enum { kPlain = 0, kGaussian = 1, kCategorical = 2 };  // epilogue of mlp_forward_kernel
+
 struct PolicyOut {
-    const float* eps;  // [rows, A] or nullptr
+    const float* eps;  // [rows, A] or nullptr (Gaussian: N(0,1); categorical: Exp(1))
     uint64_t seed, step;
+    const uint64_t* step_base;  // optional device counter added to `step` (CUDA-graph replays)
     int64_t env_offset;
     float* action;
     float* logprob;
     float* env_action;
+    int32_t* action_index;  // categorical
 };
 
-template <int TB, bool POLICY>
+template <int TB, int POLICY>
 __global__ void __launch_bounds__(kFwdThreads)
 mlp_forward_kernel(const __grid_constant__ b200rl_net net, const float* __restrict__ x, int64_t rows, float* out,
                    int out_tanh, int buf_floats, const __grid_constant__ PolicyOut po) {
@@ -37,7 +41,8 @@ mlp_forward_kernel(const __grid_constant__ b200rl_net net, const float* __restri
         float* t = cur; cur = nxt; nxt = t;
     }
     const int J = net.dims[L];
-    if (!POLICY) {
+    const uint64_t rng_step = (POLICY != kPlain && po.step_base) ? po.step + *po.step_base : po.step;
+    if (POLICY == kPlain) {
         for (int idx = threadIdx.x; idx < TB * J; idx += kFwdThreads) {
             int b = idx / J, j = idx - b * J;
             int64_t row = row0 + b;
@@ -45,6 +50,36 @@ mlp_forward_kernel(const __grid_constant__ b200rl_net net, const float* __restri
                 float v = cur[T::elem(j, b)];
                 out[row * J + j] = out_tanh ? tanhf(v) : v;
             }
+        }
+    } else if (POLICY == kCategorical) {
+        // ActorDiscretePPO.get_action (reference AgentPPO.py:407-413): softmax -> Categorical.sample() -> log_prob.
+        // torch.multinomial's one-draw path is argmax(p / q), q ~ Exp(1); the first maximum wins ties (argmax).
+        const int b = threadIdx.x;
+        const int64_t row = row0 + b;
+        if (b < TB && row < rows) {
+            float m = -INFINITY;
+            for (int a = 0; a < J; ++a) m = fmaxf(m, cur[T::elem(a, b)]);
+            float sum = 0.0f;
+            for (int a = 0; a < J; ++a) sum += expf(cur[T::elem(a, b)] - m);
+            const float inv_sum = 1.0f / sum;
+            float best = -1.0f, best_p = 0.0f;
+            int best_a = 0;
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            for (int a = 0; a < J; ++a) {
+                const float p = expf(cur[T::elem(a, b)] - m) * inv_sum;
+                float q;
+                if (po.eps) {
+                    q = po.eps[row * J + a];
+                } else {
+                    if ((a & 3) == 0) bits = rollout_bits(po.seed, (uint64_t)(po.env_offset + row), rng_step, (uint32_t)(a >> 2));
+                    const uint32_t w = (a & 3) == 0 ? bits.x : (a & 3) == 1 ? bits.y : (a & 3) == 2 ? bits.z : bits.w;
+                    q = -logf(u32_to_unit_open(w));
+                }
+                const float race = __fdiv_rn(p, q);
+                if (race > best) { best = race; best_a = a; best_p = p; }
+            }
+            po.action_index[row] = best_a;
+            po.logprob[row] = logf(best_p);
         }
     } else {
         // a = mu + sigma * eps; logprob = sum_a Normal(mu, sigma).log_prob(a)   (torch op order, no contraction)
@@ -59,7 +94,7 @@ mlp_forward_kernel(const __grid_constant__ b200rl_net net, const float* __restri
                 if (po.eps) {
                     e = po.eps[row * J + a];
                 } else {
-                    RolloutNoise nz = rollout_noise(po.seed, (uint64_t)(po.env_offset + row), po.step, (uint32_t)(a >> 1));
+                    RolloutNoise nz = rollout_noise(po.seed, (uint64_t)(po.env_offset + row), rng_step, (uint32_t)(a >> 1));
                     e = (a & 1) ? nz.normal.y : nz.normal.x;
                 }
                 float act = __fadd_rn(__fmul_rn(e, sd), mu);
@@ -75,7 +110,7 @@ mlp_forward_kernel(const __grid_constant__ b200rl_net net, const float* __restri
     }
 }
 
-template <bool POLICY>
+template <int POLICY>
 int launch_forward(const b200rl_net* net, const float* x, int64_t rows, float* out, int out_tanh, const PolicyOut& po,
                    cudaStream_t stream) {
     if (rows <= 0) return 0;
@@ -107,13 +142,17 @@ int launch_forward(const b200rl_net* net, const float* x, int64_t rows, float* o
 
 }  // namespace
 
+thread_local const uint64_t* t_step_base = nullptr;
+
 extern "C" {
+
+void b200rl_set_policy_step_base(const uint64_t* step_base) { t_step_base = step_base; }
 
 int b200rl_mlp_forward(const b200rl_net* net, const float* x, int64_t rows, float* out, int32_t out_tanh, void* stream) {
     if (int rc = b200rl_validate_net(net, "mlp_forward", false)) return rc;
     B200RL_REQUIRE(x && out, "mlp_forward: x/out is NULL");
     PolicyOut po{};
-    return launch_forward<false>(net, x, rows, out, out_tanh, po, (cudaStream_t)stream);
+    return launch_forward<kPlain>(net, x, rows, out, out_tanh, po, (cudaStream_t)stream);
 }
 
 int b200rl_policy_step(const b200rl_net* actor, const b200rl_net* critic, const float* state, int64_t rows,
@@ -121,13 +160,30 @@ int b200rl_policy_step(const b200rl_net* actor, const b200rl_net* critic, const 
                        float* logprob, float* env_action, float* value, void* stream) {
     if (int rc = b200rl_validate_net(actor, "policy_step.actor", true)) return rc;
     B200RL_REQUIRE(state && action && logprob && env_action, "policy_step: NULL buffer");
-    PolicyOut po{eps, seed, step, env_offset, action, logprob, env_action};
-    if (int rc = launch_forward<true>(actor, state, rows, nullptr, 0, po, (cudaStream_t)stream)) return rc;
+    PolicyOut po{eps, seed, step, t_step_base, env_offset, action, logprob, env_action, nullptr};
+    if (int rc = launch_forward<kGaussian>(actor, state, rows, nullptr, 0, po, (cudaStream_t)stream)) return rc;
     if (critic && value) {
         if (int rc = b200rl_validate_net(critic, "policy_step.critic", false)) return rc;
         B200RL_REQUIRE(critic->dims[critic->num_linear] == 1, "policy_step: critic output dim must be 1");
         PolicyOut none{};
-        return launch_forward<false>(critic, state, rows, value, 0, none, (cudaStream_t)stream);
+        return launch_forward<kPlain>(critic, state, rows, value, 0, none, (cudaStream_t)stream);
+    }
+    return 0;
+}
+
+int b200rl_policy_step_discrete(const b200rl_net* actor, const b200rl_net* critic, const float* state, int64_t rows,
+                                const float* expo, uint64_t seed, uint64_t step, int64_t env_offset, int32_t* action,
+                                float* logprob, float* value, void* stream) {
+    if (int rc = b200rl_validate_net(actor, "policy_step_discrete.actor", false)) return rc;
+    B200RL_REQUIRE(actor->action_std_log == nullptr, "policy_step_discrete: a categorical actor has no action_std_log");
+    B200RL_REQUIRE(state && action && logprob, "policy_step_discrete: NULL buffer");
+    PolicyOut po{expo, seed, step, t_step_base, env_offset, nullptr, logprob, nullptr, action};
+    if (int rc = launch_forward<kCategorical>(actor, state, rows, nullptr, 0, po, (cudaStream_t)stream)) return rc;
+    if (critic && value) {
+        if (int rc = b200rl_validate_net(critic, "policy_step_discrete.critic", false)) return rc;
+        B200RL_REQUIRE(critic->dims[critic->num_linear] == 1, "policy_step_discrete: critic output dim must be 1");
+        PolicyOut none{};
+        return launch_forward<kPlain>(critic, state, rows, value, 0, none, (cudaStream_t)stream);
     }
     return 0;
 }

@@ -352,11 +352,19 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
         }
     }
     __syncthreads();
+    const bool discrete = A.buf.discrete_actions != 0;
     {
-        const int Adim = A.net[0].dims[A.net[0].num_linear];
+        // discrete (AgentDiscretePPO): ONE int32 action index per transition, kept as a float in action slot 0
+        const int Adim = discrete ? 1 : A.net[0].dims[A.net[0].num_linear];
         for (int idx = threadIdx.x; idx < UTB * Adim; idx += kUpdThreads) {
             int b = idx / Adim, a = idx - b * Adim;
-            s_act[a * UTB + b] = s_tn[b] < 0 ? 0.0f : (packed ? A.buf.states[s_tn[b] * rec + rec_act + a] : A.buf.actions[s_tn[b] * Adim + a]);
+            float v = 0.0f;
+            if (s_tn[b] >= 0) {
+                if (packed) v = A.buf.states[s_tn[b] * rec + rec_act + a];
+                else if (discrete) v = (float)reinterpret_cast<const int32_t*>(A.buf.actions)[s_tn[b]];
+                else v = A.buf.actions[s_tn[b] * Adim + a];
+            }
+            s_act[a * UTB + b] = v;
         }
     }
     const float inv_bsz = 1.0f / (float)A.global_batch;
@@ -417,13 +425,27 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
             dzA[UT::elem(0, b)] = valid ? dl * um_c * inv_bsz : 0.0f;
         } else {
             // new_logprob, ratio, clip, entropy                           (:193-203; helloworld :335-340)
-            float logp = 0.0f, ent = 0.0f;
-            for (int a = 0; a < OUT; ++a) {
-                float sd = expf(ld_param<WM>(std_log + a));
-                float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
-                float lsd = logf(sd);
-                logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
-                ent += 0.5f + kLogSqrt2Pi + lsd;  // 0.5 + 0.5 log(2 pi) + log(scale)
+            float logp = 0.0f, ent = 0.0f, lse = 0.0f;
+            const int act_idx = discrete ? min(max((int)s_act[b], 0), OUT - 1) : 0;
+            if (discrete) {
+                // Categorical(softmax(logits)): logp = log p[a], entropy = -sum p log p   (reference :415-421)
+                float m = -INFINITY, sum = 0.0f;
+                for (int a = 0; a < OUT; ++a) m = fmaxf(m, dzA[UT::elem(a, b)]);
+                for (int a = 0; a < OUT; ++a) sum += expf(dzA[UT::elem(a, b)] - m);
+                lse = m + logf(sum);
+                for (int a = 0; a < OUT; ++a) {
+                    const float lp = dzA[UT::elem(a, b)] - lse;
+                    ent -= expf(lp) * lp;
+                }
+                logp = dzA[UT::elem(act_idx, b)] - lse;
+            } else {
+                for (int a = 0; a < OUT; ++a) {
+                    float sd = expf(ld_param<WM>(std_log + a));
+                    float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
+                    float lsd = logf(sd);
+                    logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
+                    ent += 0.5f + kLogSqrt2Pi + lsd;  // 0.5 + 0.5 log(2 pi) + log(scale)
+                }
             }
             const float ratio = expf(logp - s_logp[b]);
             const float adv = s_adv[b];
@@ -448,14 +470,23 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
             // (:203-204), helloworld adds it (:340)
             const float ent_sign = (flags & B200RL_PPO_ENTROPY_BONUS) ? -1.0f : 1.0f;  // sign of d loss / d entropy
             const float gl = valid ? -(dsurr_dratio * ratio * um_a) * inv_bsz : 0.0f;  // d loss / d new_logprob
-            for (int a = 0; a < OUT; ++a) {
-                float sd = expf(ld_param<WM>(std_log + a));
-                float var = sd * sd;
-                float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
-                dzA[UT::elem(a, b)] = gl * diff / var;
-                float dstd = gl * (diff * diff / var - 1.0f) + (valid ? ent_sign * A.hp.lambda_entropy * um_a * inv_bsz : 0.0f);
-                dstd = warp_sum(dstd);  // UTB == 32: exactly warp 0
-                if (b == 0) atomicAdd(g + A.grad_numel[0] - OUT + a, dstd);
+            const float ge = valid ? ent_sign * A.hp.lambda_entropy * um_a * inv_bsz : 0.0f;  // d loss / d entropy
+            if (discrete) {
+                // d logp[a*] / d z_j = [j == a*] - p_j;   d entropy / d z_j = -p_j (log p_j + entropy)
+                for (int a = 0; a < OUT; ++a) {
+                    const float lp = dzA[UT::elem(a, b)] - lse, pa = expf(lp);
+                    dzA[UT::elem(a, b)] = gl * ((a == act_idx ? 1.0f : 0.0f) - pa) - ge * pa * (lp + ent);
+                }
+            } else {
+                for (int a = 0; a < OUT; ++a) {
+                    float sd = expf(ld_param<WM>(std_log + a));
+                    float var = sd * sd;
+                    float diff = s_act[a * UTB + b] - dzA[UT::elem(a, b)];
+                    dzA[UT::elem(a, b)] = gl * diff / var;
+                    float dstd = gl * (diff * diff / var - 1.0f) + ge;
+                    dstd = warp_sum(dstd);  // UTB == 32: exactly warp 0
+                    if (b == 0) atomicAdd(g + A.grad_numel[0] - OUT + a, dstd);
+                }
             }
         }
     }
@@ -574,8 +605,13 @@ __global__ void pack_minibatches_kernel(const b200rl_train_buffer buf, int S, in
     const int tail = (S + Adim + 3) & ~3;
     float* r = out + (size_t)i * (tail + 4);
     for (int k = 0; k < S; ++k) r[k] = buf.states[tn * S + k];
-    for (int a = 0; a < Adim; ++a) r[S + a] = buf.actions[tn * Adim + a];
-    for (int k = S + Adim; k < tail; ++k) r[k] = 0.0f;
+    if (buf.discrete_actions) {  // one int32 index per transition -> float in slot 0, the other action slots stay zero
+        r[S] = (float)reinterpret_cast<const int32_t*>(buf.actions)[tn];
+        for (int k = S + 1; k < tail; ++k) r[k] = 0.0f;
+    } else {
+        for (int a = 0; a < Adim; ++a) r[S + a] = buf.actions[tn * Adim + a];
+        for (int k = S + Adim; k < tail; ++k) r[k] = 0.0f;
+    }
     float adv = buf.advantages[tn];
     if (buf.adv_stats) adv = (adv - buf.adv_stats[0]) / (buf.adv_stats[1] + 1e-5f);
     r[tail + 0] = buf.unmasks[tn] ? 1.0f : 0.0f;
@@ -601,7 +637,11 @@ AdamScalars adam_scalars(const b200rl_adam* opt, int64_t step) {
 int fill_args(UpdateArgs& A, const b200rl_net* actor, const b200rl_net* critic, const b200rl_adam* actor_opt,
               const b200rl_adam* critic_opt, const b200rl_train_buffer* buffer, const b200rl_ppo_hyper* hyper,
               void* workspace, int64_t workspace_bytes, size_t* smem_bytes) {
-    if (int rc = b200rl_validate_net(actor, "ppo.actor", true)) return rc;
+    // (b200rl_ppo_apply passes no buffer: there the actor's own layout decides)
+    const bool discrete = buffer ? buffer->discrete_actions != 0 : (actor && actor->action_std_log == nullptr);
+    if (int rc = b200rl_validate_net(actor, "ppo.actor", !discrete)) return rc;
+    B200RL_REQUIRE(!discrete || actor->action_std_log == nullptr,
+                   "ppo: discrete_actions needs a categorical actor (action_std_log must be NULL)");
     if (int rc = b200rl_validate_net(critic, "ppo.critic", false)) return rc;
     B200RL_REQUIRE(hyper && workspace, "ppo: hyper/workspace is NULL");
     B200RL_REQUIRE(critic->dims[critic->num_linear] == 1, "ppo: critic output dim must be 1");

@@ -47,7 +47,8 @@ typedef struct b200rl_net {
     float* bias[B200RL_MAX_LINEAR];       /* [dims[l+1]] */
     const float* state_avg;               /* [dims[0]] or NULL: no state_norm at all (helloworld) */
     const float* state_std;               /* [dims[0]]; normalised input = (s - avg) / (std + 1e-4) */
-    float* action_std_log;                /* actor: [action_dim] (ActorPPO.action_std_log); critic: NULL */
+    float* action_std_log;                /* Gaussian actor: [action_dim] (ActorPPO.action_std_log); critic and the
+                                             categorical actor (ActorDiscretePPO, AgentPPO.py:393-425): NULL */
 } b200rl_net;
 
 /* torch.optim.Adam state of one net (reference AgentPPO.py:24-25; stepped by AgentBase.py:239-248), tensor
@@ -82,7 +83,7 @@ typedef struct b200rl_ppo_hyper {
  * (states, actions, unmasks, logprobs, advantages, reward_sums), time-major [H, N, ...]. */
 typedef struct b200rl_train_buffer {
     const float* states;                  /* [H, N, S] */
-    const float* actions;                 /* [H, N, A] */
+    const float* actions;                 /* [H, N, A] fp32; int32 [H, N] action indices when discrete_actions != 0 */
     const uint8_t* unmasks;               /* [H, N] bool */
     const float* logprobs;                /* [H, N] */
     const float* advantages;              /* [H, N] */
@@ -92,6 +93,12 @@ typedef struct b200rl_train_buffer {
                                              normalised (reference :149) */
     int32_t horizon_len;                  /* H */
     int32_t num_envs;                     /* N */
+    int32_t discrete_actions;             /* != 0: AgentDiscretePPO (AgentPPO.py:252-270, 103-104): `actions` holds int32
+                                             indices [H, N], the actor's outputs are logits of a Categorical
+                                             (log-prob / entropy of ActorDiscretePPO.get_logprob_entropy :415-421) and
+                                             the actor net carries no action_std_log.  Packed records keep the index as
+                                             a float in the first action slot. */
+    int32_t reserved;
 } b200rl_train_buffer;
 
 /* Fused rollout on the built-in Pendulum-v1 vec env: replaces the Python loop of
@@ -148,6 +155,19 @@ B200RL_API int b200rl_mlp_forward(const b200rl_net* net, const float* x, int64_t
 B200RL_API int b200rl_policy_step(const b200rl_net* actor, const b200rl_net* critic, const float* state, int64_t rows,
                        const float* eps, uint64_t seed, uint64_t step, int64_t env_offset, float* action,
                        float* logprob, float* env_action, float* value, void* stream);
+/* Optional device-resident Philox step base for the two policy-step entry points: when set (non-NULL), the kernels use
+ * step + *step_base.  A caller that captures its rollout loop in a CUDA graph keeps the counter in device memory and
+ * advances it inside the graph, so that every replay draws fresh noise.  Host-side, per calling thread; NULL resets. */
+B200RL_API void b200rl_set_policy_step_base(const uint64_t* step_base);
+
+/* The same for the categorical policy: ActorDiscretePPO.get_action (AgentPPO.py:407-413) -- softmax, one draw of
+ * torch.multinomial (its single-sample path is the exponential race argmax(p / q), q ~ Exp(1)), log-prob of the drawn
+ * index.  expo [rows, A] injected Exp(1) noise or NULL (Philox).  Outputs: action int32 [rows] (what
+ * convert_action_for_env :423-425 hands to env.step after .long()), logprob [rows], value [rows] (optional). */
+B200RL_API int b200rl_policy_step_discrete(const b200rl_net* actor, const b200rl_net* critic, const float* state,
+                                           int64_t rows, const float* expo, uint64_t seed, uint64_t step,
+                                           int64_t env_offset, int32_t* action, float* logprob, float* value,
+                                           void* stream);
 
 B200RL_API int b200rl_rollout_pendulum(const b200rl_rollout_args* args, void* stream);
 

@@ -20,14 +20,15 @@ from elegantrl_b200.envs import PendulumVecEnv
 class CpuPPO:
     def __init__(self, net_dims, state_dim, action_dim, num_envs, *, gamma=0.99, lambda_gae_adv=0.95, ratio_clip=0.25,
                  lambda_entropy=0.001, clip_grad_norm=3.0, learning_rate=6e-5, reward_scale=1.0, batch_size=128,
-                 repeat_times=8.0, if_use_v_trace=True):
+                 repeat_times=8.0, if_use_v_trace=True, device="cpu"):
+        self.device = th.device(device)  # "cuda:0" turns the same op sequence into the eager PyTorch-CUDA baseline
         self.state_dim, self.action_dim, self.num_envs = state_dim, action_dim, num_envs
         self.gamma, self.lambda_gae_adv, self.ratio_clip = gamma, lambda_gae_adv, ratio_clip
-        self.lambda_entropy = th.tensor(lambda_entropy, dtype=th.float32)
+        self.lambda_entropy = th.tensor(lambda_entropy, dtype=th.float32, device=self.device)
         self.clip_grad_norm, self.reward_scale = clip_grad_norm, reward_scale
         self.batch_size, self.repeat_times, self.if_use_v_trace = batch_size, repeat_times, if_use_v_trace
-        self.act = ActorPPO(net_dims, state_dim, action_dim)
-        self.cri = CriticPPO(net_dims, state_dim, action_dim)
+        self.act = ActorPPO(net_dims, state_dim, action_dim).to(self.device)
+        self.cri = CriticPPO(net_dims, state_dim, action_dim).to(self.device)
         self.act_optimizer = th.optim.Adam(self.act.parameters(), learning_rate)
         self.cri_optimizer = th.optim.Adam(self.cri.parameters(), learning_rate)
         self.criterion = th.nn.MSELoss(reduction="none")
@@ -36,12 +37,13 @@ class CpuPPO:
     # ---- rollout: Python loop of H steps, ~45 ATen launches per step (:87-129, get_action :368-376)
     def explore_env(self, env, horizon_len):
         n = self.num_envs
-        states = th.zeros((horizon_len, n, self.state_dim), dtype=th.float32)
-        actions = th.zeros((horizon_len, n, self.action_dim), dtype=th.float32)
-        logprobs = th.zeros((horizon_len, n), dtype=th.float32)
-        rewards = th.zeros((horizon_len, n), dtype=th.float32)
-        terminals = th.zeros((horizon_len, n), dtype=th.bool)
-        truncates = th.zeros((horizon_len, n), dtype=th.bool)
+        dev = self.device
+        states = th.zeros((horizon_len, n, self.state_dim), dtype=th.float32).to(dev)  # (:101-107 allocate on the host first)
+        actions = th.zeros((horizon_len, n, self.action_dim), dtype=th.float32).to(dev)
+        logprobs = th.zeros((horizon_len, n), dtype=th.float32).to(dev)
+        rewards = th.zeros((horizon_len, n), dtype=th.float32).to(dev)
+        terminals = th.zeros((horizon_len, n), dtype=th.bool).to(dev)
+        truncates = th.zeros((horizon_len, n), dtype=th.bool).to(dev)
         state = self.last_state
         with th.no_grad():
             for t in range(horizon_len):
@@ -87,7 +89,7 @@ class CpuPPO:
     def update_objectives(self, buffer):
         states, actions, unmasks, logprobs, advantages, reward_sums = buffer
         sample_len, num_seqs = states.shape[0], states.shape[1]
-        ids = th.randint(sample_len * num_seqs, size=(self.batch_size,), requires_grad=False)
+        ids = th.randint(sample_len * num_seqs, size=(self.batch_size,), requires_grad=False, device=self.device)
         ids0 = th.fmod(ids, sample_len)
         ids1 = th.div(ids, sample_len, rounding_mode='floor')
         state, action, unmask = states[ids0, ids1], actions[ids0, ids1], unmasks[ids0, ids1]
@@ -128,22 +130,28 @@ class CpuPPO:
         return tuple(logs.mean(dim=0).tolist())
 
 
-def time_cpu_cycles(num_envs, horizon_len, net_dims=(64, 64), warmup=1, cycles=3, threads=None, seed=0, **hyper):
-    """Time explore_env + update_net of the port on the torch Pendulum vec env, all host threads.
+def time_cpu_cycles(num_envs, horizon_len, net_dims=(64, 64), warmup=1, cycles=3, threads=None, seed=0, device="cpu", **hyper):
+    """Time explore_env + update_net of the port on the torch Pendulum vec env, all host threads (``device="cuda:0"``:
+    the same eager op sequence on the GPU, synchronised around each phase).
     Returns dict(env_steps_per_sec, explore_s, update_s, cycle_s (lists), threads)."""
     if threads is None:
         threads = th.get_num_threads()
     th.set_num_threads(threads)
     th.manual_seed(seed)
-    agent = CpuPPO(list(net_dims), 3, 1, num_envs, **hyper)
-    env = PendulumVecEnv(num_envs=num_envs, gpu_id=-1, max_step=200, seed=seed)
+    on_gpu = th.device(device).type == "cuda"
+    sync = th.cuda.synchronize if on_gpu else (lambda: None)
+    agent = CpuPPO(list(net_dims), 3, 1, num_envs, device=device, **hyper)
+    env = PendulumVecEnv(num_envs=num_envs, gpu_id=th.device(device).index or 0 if on_gpu else -1, max_step=200, seed=seed)
     agent.last_state = env.reset()[0]
     explore_s, update_s = [], []
     for i in range(warmup + cycles):
+        sync()
         t0 = time.perf_counter()
         buffer = agent.explore_env(env, horizon_len)
+        sync()
         t1 = time.perf_counter()
         agent.update_net(list(buffer))
+        sync()
         t2 = time.perf_counter()
         if i >= warmup:
             explore_s.append(t1 - t0)

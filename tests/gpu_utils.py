@@ -53,3 +53,31 @@ def assert_close(actual, expected, rtol=1e-4, atol=1e-5, msg=""):
     if th.is_tensor(actual):
         actual = actual.detach().cpu().numpy()
     np.testing.assert_allclose(actual, expected, rtol=rtol, atol=atol, err_msg=msg)
+
+
+def discrete_agent_from_golden(g, gpu_id=0, **overrides):
+    """AgentDiscretePPO with the golden's nets (its inherited, unused action_std_log is loaded too)."""
+    from elegantrl_b200.agents import AgentDiscretePPO
+    dims = [int(x) for x in g["dims"]]
+    state_dim, action_dim, num_envs, horizon_len = dims[:4]
+    net_dims = dims[4:]
+    hp = gu.hyper_of(g)
+    env_args = {'env_name': 'golden', 'num_envs': num_envs, 'max_step': 200, 'state_dim': state_dim,
+                'action_dim': action_dim, 'if_discrete': True}
+    args = Config(agent_class=AgentDiscretePPO, env_class=None, env_args=env_args)
+    args.net_dims = net_dims
+    for k in ("gamma", "ratio_clip", "lambda_entropy", "clip_grad_norm", "learning_rate", "reward_scale",
+              "batch_size", "repeat_times", "lambda_gae_adv", "if_use_v_trace"):
+        setattr(args, k, hp[k])
+    for k, v in overrides.items():
+        setattr(args, k, v)
+    agent = AgentDiscretePPO(net_dims, state_dim, action_dim, gpu_id=gpu_id, args=args)
+    load_module(agent.act, gu.net_of(g, "actor"))
+    load_module(agent.cri, gu.net_of(g, "critic"))
+    return agent
+
+
+def discrete_module_to_net(module):
+    net = module_to_net(module)
+    net.pop("action_std_log", None)
+    return net
