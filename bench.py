@@ -300,6 +300,14 @@ def run_engine(args):
                                 "sample": f"{cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up, thread count "
                                           f"calibrated ({cb['threads']} of {os.cpu_count()} logical CPUs); "
                                           f"explore {statistics.mean(cb['explore_s']):.3f}s + update {statistics.mean(cb['update_s']):.3f}s per cycle"}
+        # the same pinned op sequence as EAGER PyTorch on this very GPU (SURVEY 8(d) "stronger baseline"): what a user of the
+        # reference gets with gpu_id=0 -- ~45 launches per env step, ~250 per minibatch.  Informational; ~2 s.
+        gb = time_cpu_cycles(NUM_ENVS, HORIZON, NET_DIMS, warmup=2, cycles=5, threads=threads, device=f"cuda:{local_rank}",
+                             batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+        line["cpu_baseline"]["eager_pytorch_same_gpu"] = {
+            "value": gb["env_steps_per_sec"], "unit": UNIT,
+            "sample": f"5 full cycles after 2 warm-ups; explore {1e3 * statistics.mean(gb['explore_s']):.1f} ms + update "
+                      f"{1e3 * statistics.mean(gb['update_s']):.1f} ms per cycle"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
