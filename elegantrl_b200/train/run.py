@@ -18,10 +18,12 @@ def evaluate_vec_env(actor, env_class, env_args, device_id: int, episodes_envs: 
     env = env_class(**{k: v for k, v in args.items() if k in ("num_envs", "max_step")}, gpu_id=device_id)
     state, _ = env.reset()
     returns = th.zeros(episodes_envs, device=state.device)
+    alive = th.ones(episodes_envs, dtype=th.bool, device=state.device)  # first episode of every sub-env only (auto-reset envs)
     with th.no_grad():
         for _ in range(env.max_step):
             state, reward, terminal, truncate, _ = env.step(actor(state))
-            returns += reward
+            returns += reward * alive
+            alive &= ~(terminal | truncate)
     return float(returns.mean()), float(returns.std())
 
 
