@@ -202,11 +202,10 @@ def run_engine(args):
         theta_dot.copy_(host_in[1], non_blocking=True)
         cur_step.copy_(host_in[2], non_blocking=True)
         buffer = agent.explore_env(env, HORIZON)             # public API
-        result = agent.update_net(list(buffer))              # public API: returns 3 Python floats (D2H + sync)
-        host_last_state.copy_(agent.last_state, non_blocking=True)
+        host_last_state.copy_(agent.last_state, non_blocking=True)   # D2H: final once the rollout is done (stream order)
         for h, d in zip(host_in, env.engine_state()):        # D2H: env state for the host-side loop
             h.copy_(d, non_blocking=True)
-        th.cuda.synchronize()
+        result = agent.update_net(list(buffer))              # public API: returns 3 Python floats (D2H + sync)
         return result
 
     for _ in range(max(args.warmup, 3)):
