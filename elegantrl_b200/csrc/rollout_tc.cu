@@ -132,18 +132,23 @@ DEV float eval_net(GroupCtx& c, const float (&x)[3], int lane) {
         }
         tc05::fence_proxy_async_smem();
         __syncwarp();
-        // warp-aggregated arrival; the last warp of the group issues the MMAs of both chunks
-        if (lane == 0) {
-            const uint32_t old = atom_add_acq_rel_smem(&c.fill[0], 1u);
-            if (old == c.group_warps * (use + 1) - 1) {
-                tc05::fence_after_thread_sync();
-                const uint32_t d = c.tmem_d & 0x0000FFFFu;  // lane 0: the MMA addresses the whole 128-lane tile
+        // warp-aggregated arrival; the last warp of the group issues the MMAs of both chunks.  The outcome is voted so that
+        // the issue code runs in warp-UNIFORM control flow (descriptors in uniform registers, one elected lane issues)
+        uint32_t old = 0u;
+        if (lane == 0) old = atom_add_acq_rel_smem(&c.fill[0], 1u);
+        const bool last = __ballot_sync(0xffffffffu, lane == 0 && old == c.group_warps * (use + 1) - 1) != 0u;
+        if (last) {
+            tc05::fence_after_thread_sync();
+            const uint32_t d = __shfl_sync(0xffffffffu, c.tmem_d, 0) & 0x0000FFFFu;  // lane field 0: the MMA addresses the whole tile
+            const uint32_t ring = __shfl_sync(0xffffffffu, c.ring_addr, 0);
+            const uint32_t bhi = __shfl_sync(0xffffffffu, c.bhi_addr, 0), blo = __shfl_sync(0xffffffffu, c.blo_addr, 0);
+            if (tc05::elect_one()) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int ch = cp * 2 + half;
-                    const uint32_t a_addr = c.ring_addr + half * kSlotBytes;
+                    const uint32_t a_addr = ring + half * kSlotBytes;
                     const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
-                    const uint64_t b_hi = tc05::make_smem_desc(c.bhi_addr + ch * 256, 2048), b_lo = tc05::make_smem_desc(c.blo_addr + ch * 256, 2048);
+                    const uint64_t b_hi = tc05::make_smem_desc(bhi + ch * 256, 2048), b_lo = tc05::make_smem_desc(blo + ch * 256, 2048);
                     tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
                     tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
                     tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
@@ -151,8 +156,8 @@ DEV float eval_net(GroupCtx& c, const float (&x)[3], int lane) {
                 tc05::mma_commit(&c.slot_free[0]);
                 if (cp == kChunks / 2 - 1) tc05::mma_commit(c.d_ready);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
     tc05::mbar_wait(c.d_ready, c.evals & 1);
     c.evals += 1;
