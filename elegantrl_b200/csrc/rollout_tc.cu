@@ -78,7 +78,8 @@ DEV uint32_t atom_add_acq_rel_smem(uint32_t* p, uint32_t v) {
 
 struct GroupCtx {
     uint32_t ring_addr;     // shared address of this group's 2-slot A ring
-    uint32_t bhi_addr, blo_addr;
+    uint32_t a_desc_lo;     // low words of the shared-memory matrix descriptors: A slot 0 hi plane, B hi / lo plane chunk 0
+    uint32_t bhi_desc_lo, blo_desc_lo;
     uint64_t* slot_free;    // [2]
     uint64_t* d_ready;
     uint32_t* fill;         // [2] arrival counters of the two ring slots (monotonic)
@@ -139,16 +140,17 @@ DEV float eval_net(GroupCtx& c, const float (&x)[3], int lane) {
         const bool last = __ballot_sync(0xffffffffu, lane == 0 && old == c.group_warps * (use + 1) - 1) != 0u;
         if (last) {
             tc05::fence_after_thread_sync();
-            const uint32_t d = __shfl_sync(0xffffffffu, c.tmem_d, 0) & 0x0000FFFFu;  // lane field 0: the MMA addresses the whole tile
-            const uint32_t ring = __shfl_sync(0xffffffffu, c.ring_addr, 0);
-            const uint32_t bhi = __shfl_sync(0xffffffffu, c.bhi_addr, 0), blo = __shfl_sync(0xffffffffu, c.blo_addr, 0);
+            const uint32_t d = c.tmem_d & 0x0000FFFFu;  // lane field 0: the MMA addresses the whole 128-lane tile
             if (tc05::elect_one()) {
+                // descriptors = precomputed low word + (byte offset >> 4); high words: SBO >> 4 | version 1 (bit 46)
+                constexpr uint64_t kHiA = (uint64_t)(0x4000u | (256u >> 4)) << 32, kHiB = (uint64_t)(0x4000u | (2048u >> 4)) << 32;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int ch = cp * 2 + half;
-                    const uint32_t a_addr = ring + half * kSlotBytes;
-                    const uint64_t a_hi = tc05::make_smem_desc(a_addr, 256), a_lo = tc05::make_smem_desc(a_addr + 4096, 256);
-                    const uint64_t b_hi = tc05::make_smem_desc(bhi + ch * 256, 2048), b_lo = tc05::make_smem_desc(blo + ch * 256, 2048);
+                    const uint64_t a_hi = kHiA | (uint64_t)(c.a_desc_lo + half * (kSlotBytes >> 4));
+                    const uint64_t a_lo = kHiA | (uint64_t)(c.a_desc_lo + half * (kSlotBytes >> 4) + (4096 >> 4));
+                    const uint64_t b_hi = kHiB | (uint64_t)(c.bhi_desc_lo + ch * (256 >> 4));
+                    const uint64_t b_lo = kHiB | (uint64_t)(c.blo_desc_lo + ch * (256 >> 4));
                     tc05::mma_tf32(d, a_hi, b_hi, idesc, ch > 0);
                     tc05::mma_tf32(d, a_lo, b_hi, idesc, true);
                     tc05::mma_tf32(d, a_hi, b_lo, idesc, true);
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
 
     GroupCtx ctx;
     ctx.ring_addr = tc05::smem_u32(smem + kOffRing + group * 2 * kSlotBytes);
-    ctx.bhi_addr = tc05::smem_u32(smem + kOffB + (net * 2 + 0) * kPlaneB);
-    ctx.blo_addr = tc05::smem_u32(smem + kOffB + (net * 2 + 1) * kPlaneB);
+    ctx.a_desc_lo = (uint32_t)tc05::make_smem_desc(ctx.ring_addr, 256);
+    ctx.bhi_desc_lo = (uint32_t)tc05::make_smem_desc(tc05::smem_u32(smem + kOffB + (net * 2 + 0) * kPlaneB), 2048);
+    ctx.blo_desc_lo = (uint32_t)tc05::make_smem_desc(tc05::smem_u32(smem + kOffB + (net * 2 + 1) * kPlaneB), 2048);
     ctx.slot_free = slot_free + group * 2;
     ctx.d_ready = d_ready + group;
     ctx.fill = fill + group * 2;
