@@ -29,7 +29,7 @@ METRIC = "env-steps/sec (rollout+GAE+update) at 65 536 envs"
 UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 17408          # actor fwd 8704 + critic fwd 8704
 HBM_BYTES_PER_ENV_STEP = 30        # 26 B trajectory + 4 B value written by the fused rollout kernel
-NCU_DRAM_BYTES_PER_LAUNCH = 194.59e6  # measured once with ncu (0.87 MB read + 193.72 MB written), profiles/r01_v4_*
+NCU_DRAM_BYTES_PER_LAUNCH = 196.41e6  # measured once with ncu (0.88 MB read + 195.53 MB written), profiles/r01_v5_*
 
 
 def workload_config(n_gpus):
@@ -275,7 +275,7 @@ def run_engine(args):
     roofline = {"kernel": "rollout_pendulum_tc_kernel (fused env + actor + critic + trajectory stores; 64x64 layers on tcgen05, 3xTF32)", "bound": "tensor",
                 "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of "
-                "one `ncu --set full` capture (profiles/r01_v4_rollout_tc_metrics.txt); algorithmic 251.9e6 written, the tail "
+                "one `ncu --set full` capture (profiles/r01_v5_rollout_tc_metrics.txt); algorithmic 251.9e6 written, the tail "
                 "of the trajectory is still in L2 when the kernel ends", "peak_source": peaks["source"], "avg_launch_ms": rollout_ms,
                 "launch_ms_min_max": [min(rollout_list), max(rollout_list)],
                 "share_of_step": rollout_ms / (elapsed_ms / args.steps),
