@@ -582,3 +582,32 @@ def test_fused_rollout_long_horizon(rollout_impl):
     tr = np.argwhere(want_trunc[:-1])
     got_thd = states[1:, :, 2].cpu().numpy()[tr[:, 0], tr[:, 1]]
     np.testing.assert_array_equal(got_thd, (reset_u[tr[:, 0], tr[:, 1], 1] * np.float32(2.0) - np.float32(1.0)))
+
+
+@pytest.mark.parametrize("batch", [148 * 32, 9472 + 32, 20000])
+def test_large_minibatch_against_oracle(batch):
+    """Minibatches above 296 tiles: every CTA of b200rl_ppo_update's per-minibatch kernel walks several 32-sample tiles and
+    sums its weight gradients in shared memory before one RED.ADD per element.  Two updates against the numpy oracle."""
+    g = gu.load("synth_s3_a1_64x64")
+    agent = G.agent_from_golden(g, batch_size=batch)
+    rng = np.random.default_rng(batch)
+    h, n = 64, 512
+    states = rng.standard_normal((h, n, 3)).astype(np.float32)
+    actions = (0.7 * rng.standard_normal((h, n, 1))).astype(np.float32)
+    actor, critic = gu.net_of(g, "actor"), gu.net_of(g, "critic")
+    logprobs = (po.logprob_entropy(actor, states.reshape(-1, 3), actions.reshape(-1, 1))[0].reshape(h, n)
+                + 0.05 * rng.standard_normal((h, n))).astype(np.float32)
+    unmasks = rng.random((h, n)) > 0.05
+    adv = rng.standard_normal((h, n)).astype(np.float32)
+    rsum = rng.standard_normal((h, n)).astype(np.float32)
+    ids = rng.integers(0, h * n, size=(2, batch)).astype(np.int64)
+    buffer = [G.cuda(x) for x in (states, actions, unmasks, logprobs, adv, rsum)]
+    scalars = _run_ppo_update(agent, buffer, G.cuda(ids))
+    hp = gu.hyper_of(g)
+    opt_a, opt_c = po.new_adam_state(actor, True), po.new_adam_state(critic, False)
+    buf = dict(states=states, actions=actions, unmasks=unmasks, logprobs=logprobs, advantages=adv, reward_sums=rsum)
+    want = [po.ppo_minibatch(actor, critic, opt_a, opt_c, po.gather_minibatch(buf, ids[u]), hp)[0] for u in range(2)]
+    G.assert_close(scalars, np.mean(np.array(want), axis=0), RTOL, 2e-6)
+    for which, module, net in (("actor", agent.act, actor), ("critic", agent.cri, critic)):
+        for a, b in zip(gu.flat_params(G.module_to_net(module)), gu.flat_params(net)):
+            G.assert_close(a, b, RTOL, 2e-6, which)
