@@ -558,7 +558,7 @@ def ppo_minibatch_grads(actor, critic, batch, hp, denominator=None):
     local = batch["state"].shape[0]
     denominator = local if denominator is None else denominator
     hp_raw = dict(hp, clip_grad_norm=0.0, learning_rate=0.0)
-    scalars, grads = ppo_minibatch(a2, c2, new_adam_state(a2, True), new_adam_state(c2, False), batch, hp_raw)
+    scalars, grads = ppo_minibatch(a2, c2, new_adam_state(a2, not hp.get("discrete", False)), new_adam_state(c2, False), batch, hp_raw)
     scale = dt.type(local / denominator)  # ppo_minibatch averaged over the local samples
     return tuple(s * float(scale) for s in scalars), [g * scale for g in grads["actor"]], [g * scale for g in grads["critic"]]
 
@@ -571,9 +571,10 @@ def ppo_apply_grads(actor, critic, opt_a, opt_c, grads_actor, grads_critic, hp):
     mc = [p for pair in zip(opt_c["m_W"], opt_c["m_b"]) for p in pair]
     vc = [p for pair in zip(opt_c["v_W"], opt_c["v_b"]) for p in pair]
     opt_c["step"] = adam_step(pc, gc, mc, vc, opt_c["step"], hp["learning_rate"])
-    pa = [p for pair in zip(actor["W"], actor["b"]) for p in pair] + [actor["action_std_log"]]
-    ma = [p for pair in zip(opt_a["m_W"], opt_a["m_b"]) for p in pair] + [opt_a["m_std"]]
-    va = [p for pair in zip(opt_a["v_W"], opt_a["v_b"]) for p in pair] + [opt_a["v_std"]]
+    discrete = hp.get("discrete", False)
+    pa = [p for pair in zip(actor["W"], actor["b"]) for p in pair] + ([] if discrete else [actor["action_std_log"]])
+    ma = [p for pair in zip(opt_a["m_W"], opt_a["m_b"]) for p in pair] + ([] if discrete else [opt_a["m_std"]])
+    va = [p for pair in zip(opt_a["v_W"], opt_a["v_b"]) for p in pair] + ([] if discrete else [opt_a["v_std"]])
     opt_a["step"] = adam_step(pa, ga, ma, va, opt_a["step"], hp["learning_rate"])
 
 

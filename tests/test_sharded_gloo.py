@@ -11,6 +11,7 @@ import os
 import tempfile
 
 import numpy as np
+import pytest
 import torch as th
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -18,16 +19,18 @@ import torch.multiprocessing as mp
 from oracle import ppo_oracle as po
 from tests import golden_utils as gu
 
-CASE = "synth_s8_a2_128x64"
+CASES = ["synth_s8_a2_128x64", "discrete_s8_a4_128x64"]  # Gaussian policy; categorical policy (ragged shards: 9 envs)
 
 
-def _worker(rank, world, init_file, out_dir):
+def _worker(rank, world, init_file, out_dir, case):
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
-    g = gu.load(CASE)
-    hp = gu.hyper_of(g)
+    g = gu.load(case)
+    discrete = case.startswith("discrete")
+    hp = dict(gu.hyper_of(g), discrete=discrete)
+    actor_of = gu.discrete_net_of if discrete else gu.net_of
     h, n = g["buf.states"].shape[:2]
-    shard = n // world
-    lo = rank * shard
+    lo = rank * (n // world)
+    shard = n - lo if rank == world - 1 else n // world
 
     # ---- (1) advantage statistics from shard sums
     sums = th.from_numpy(po.lattice_stat_sums(g["gae.advantages"][:, lo:lo + shard], lo))
@@ -36,8 +39,8 @@ def _worker(rank, world, init_file, out_dir):
     np.testing.assert_allclose([mean, std], [g["gae.adv_mean"], g["gae.adv_std"]], rtol=1e-5, atol=1e-7)
 
     # ---- (2) one minibatch: every rank takes the samples of the golden minibatch that live in its shard
-    actor, critic = gu.net_of(g, "actor"), gu.net_of(g, "critic")
-    opt_a, opt_c = po.new_adam_state(actor, True), po.new_adam_state(critic, False)
+    actor, critic = actor_of(g, "actor"), gu.net_of(g, "critic")
+    opt_a, opt_c = po.new_adam_state(actor, not discrete), po.new_adam_state(critic, False)
     buffer = dict(states=g["buf.states"], actions=g["buf.actions"], unmasks=g["buf.unmasks"], logprobs=g["buf.logprobs"],
                   advantages=g["gae.adv_norm"], reward_sums=g["gae.reward_sums"])
     ids = g["update.ids"][0]
@@ -57,16 +60,18 @@ def _worker(rank, world, init_file, out_dir):
     np.testing.assert_allclose(flat[off:off + 3], g["update.scalars"][0], rtol=1e-4, atol=1e-6)
     po.ppo_apply_grads(actor, critic, opt_a, opt_c, ga_r, gc_r, hp)
     for which, net in (("actor", actor), ("critic", critic)):
-        for mine_p, ref in zip(gu.flat_params(net), gu.flat_params(gu.net_of(g, f"update.after1.{which}"))):
+        ref_net = (actor_of if which == "actor" else gu.net_of)(g, f"update.after1.{which}")
+        for mine_p, ref in zip(gu.flat_params(net), gu.flat_params(ref_net)):
             np.testing.assert_allclose(mine_p, ref, rtol=1e-4, atol=1e-6)
     np.save(os.path.join(out_dir, f"w_{rank}.npy"), np.concatenate([p.ravel() for p in gu.flat_params(actor)]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_env_sharded_update_matches_single_process():
+@pytest.mark.parametrize("case", CASES)
+def test_env_sharded_update_matches_single_process(case):
     with tempfile.TemporaryDirectory() as d:
         init_file = os.path.join(d, "init")
-        mp.spawn(_worker, args=(2, init_file, d), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, init_file, d, case), nprocs=2, join=True)
         w0, w1 = np.load(os.path.join(d, "w_0.npy")), np.load(os.path.join(d, "w_1.npy"))
         assert np.array_equal(w0, w1), "ranks must end with bit-identical parameters"
