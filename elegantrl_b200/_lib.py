@@ -38,6 +38,7 @@ class PPOHyper(C.Structure):
 
 PPO_SMOOTH_L1, PPO_MIN_CLIP, PPO_ENTROPY_BONUS, PPO_ACTOR_UNMASKED, PPO_CRITIC_MASK_MEAN = 1, 2, 4, 8, 16
 PPO_HELLOWORLD = PPO_SMOOTH_L1 | PPO_MIN_CLIP | PPO_ENTROPY_BONUS | PPO_ACTOR_UNMASKED | PPO_CRITIC_MASK_MEAN
+PPO_A2C = 32  # AgentA2C's actor objective (no ratio / clip); used together with PPO_ACTOR_UNMASKED and lambda_entropy = 0
 
 
 class TrainBuffer(C.Structure):

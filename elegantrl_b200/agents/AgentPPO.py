@@ -581,3 +581,30 @@ class AgentDiscretePPO(AgentPPO):
             args.if_discrete = True
         super().__init__(net_dims, state_dim, action_dim, gpu_id, args)
         self.lambda_entropy = getattr(args, "lambda_entropy", 0.01)
+
+
+class AgentA2C(AgentPPO):
+    """Drop-in for the reference's ``AgentA2C`` (``elegantrl/agents/AgentPPO.py:252-311``): PPO's rollout / GAE pass with the
+    plain policy-gradient actor objective ``(advantage * new_logprob).mean()`` (no ratio, no clip, no entropy term, not
+    masked) and ``update_net`` returning ``(obj_critic, obj_actor, 0)``.  The reference's ``update_objectives`` indexes the
+    time axis only and is coherent for single-env buffers ``[H, 1, ...]``, so this class asserts
+    ``num_envs == 1`` in ``update_net``; use ``AgentPPO`` for vec envs."""
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int, gpu_id: int = 0, args=None):
+        super().__init__(net_dims, state_dim, action_dim, gpu_id, args)
+        self._ppo_flags = _lib.PPO_A2C | _lib.PPO_ACTOR_UNMASKED
+
+    def update_net_device(self, buffer) -> TEN:
+        assert buffer[0].shape[1] == 1, "AgentA2C follows the reference: single-env buffers [H, 1, ...] only"
+        lambda_entropy, self.lambda_entropy = self.lambda_entropy, 0.0  # the A2C objective has no entropy term
+        try:
+            out = super().update_net_device(buffer)
+        finally:
+            self.lambda_entropy = lambda_entropy
+        out[2] = 0.0  # reference returns a literal 0 in the third slot (AgentPPO.py:292)
+        return out
+
+
+class AgentDiscreteA2C(AgentDiscretePPO):
+    """The reference's ``AgentDiscreteA2C`` (``AgentPPO.py:330-342``) derives from ``AgentDiscretePPO`` and inherits its
+    ``update_objectives`` unchanged: it IS discrete PPO under another name."""

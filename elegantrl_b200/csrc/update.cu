@@ -477,12 +477,19 @@ DEV void grads_phase(const UpdateArgs& A, int tile, int ni, const int64_t* ids, 
                 surr = adv * ratio * kappa;
                 dsurr_dratio = adv * kappa;
             }
+            float dlogp_scale = ratio;  // d ratio / d new_logprob
+            if (flags & B200RL_PPO_A2C) {
+                // AgentA2C (reference AgentPPO.py:309): (advantage [B,1] * new_logprob [B,A]).mean() = mean_b(adv * logp) / A
+                surr = adv * logp / (float)OUT;
+                dsurr_dratio = adv / (float)OUT;
+                dlogp_scale = 1.0f;
+            }
             loss_s = valid ? surr * um_a : 0.0f;
             loss_e = valid ? ent * um_a : 0.0f;
             // loss = -(obj_surrogate -/+ lambda_entropy * obj_entropy): the reference subtracts the entropy term
             // (:203-204), helloworld adds it (:340)
             const float ent_sign = (flags & B200RL_PPO_ENTROPY_BONUS) ? -1.0f : 1.0f;  // sign of d loss / d entropy
-            const float gl = valid ? -(dsurr_dratio * ratio * um_a) * inv_bsz : 0.0f;  // d loss / d new_logprob
+            const float gl = valid ? -(dsurr_dratio * dlogp_scale * um_a) * inv_bsz : 0.0f;  // d loss / d new_logprob
             const float ge = valid ? ent_sign * A.hp.lambda_entropy * um_a * inv_bsz : 0.0f;  // d loss / d entropy
             if (discrete) {
                 // d logp[a*] / d z_j = [j == a*] - p_j;   d entropy / d z_j = -p_j (log p_j + entropy)

@@ -78,6 +78,9 @@ typedef struct b200rl_ppo_hyper {
 #define B200RL_PPO_ACTOR_UNMASKED 8  /* actor terms are not multiplied by unmask (:339-340) */
 #define B200RL_PPO_CRITIC_MASK_MEAN 16 /* critic loss weighted by mean(unmask) of the minibatch: the [B] x [B, 1]
                                           broadcast of (:325, 332) averages to mean(loss) * mean(unmask) */
+#define B200RL_PPO_A2C 32            /* AgentA2C.update_objectives (elegantrl/agents/AgentPPO.py:306-311): obj_actor =
+                                          mean over [B, A] of advantage * new_logprob -- no ratio, no clip; callers also set
+                                          ACTOR_UNMASKED and lambda_entropy = 0.  Coherent for single-env buffers only */
 
 /* The training buffer of AgentPPO.update_net after the GAE pass (reference AgentPPO.py:151):
  * (states, actions, unmasks, logprobs, advantages, reward_sums), time-major [H, N, ...]. */

@@ -534,3 +534,55 @@ def main_discrete():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "discrete"):
     main_discrete()
+
+
+# --------------------------------------------------------------------------- A2C, single-env buffers
+def case_a2c(name, state_dim, action_dim, net_dims, horizon_len, seed, **hyper):
+    """AgentA2C (AgentPPO.py:252-311) on a synthetic single-env buffer [H, 1, ...] (the only shape its time-only indexing
+    handles): full update_net with the CPU-drawn time indices replayed."""
+    from elegantrl.agents import AgentA2C as RefAgentA2C
+    out = {}
+    th.manual_seed(seed)
+    env_args = {'env_name': 'golden', 'num_envs': 1, 'max_step': 200, 'state_dim': state_dim, 'action_dim': action_dim,
+                'if_discrete': False}
+    args = RefConfig(agent_class=RefAgentA2C, env_class=None, env_args=env_args)
+    args.net_dims = list(net_dims)
+    for k, v in hyper.items():
+        setattr(args, k, v)
+    agent = RefAgentA2C(list(net_dims), state_dim, action_dim, gpu_id=-1, args=args)
+    perturb_nets(agent, seed + 1, norm_stats=True)
+    record_hyper(agent, out)
+    out["dims"] = np.array([state_dim, action_dim, 1, horizon_len] + list(net_dims), dtype=np.int64)
+    dump_net("actor", agent.act, out)
+    dump_net("critic", agent.cri, out)
+    buf = synth_buffer(agent, horizon_len, 1, seed + 3)
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks", "last_state"), buf):
+        out[f"buf.{k}"] = t.numpy().copy()
+    record_gae(agent, buf, out, "gae")
+    agent2 = copy.deepcopy(agent)
+    states, actions, logprobs, rewards, undones, unmasks, last_state = [t.clone() for t in buf]
+    agent2.last_state = last_state
+    update_times = int(horizon_len * agent2.repeat_times / agent2.batch_size)
+    th.manual_seed(seed + 5)
+    ids = th.stack([th.randint(horizon_len, size=(agent2.batch_size,)) for _ in range(update_times)])
+    out["update_net.ids"] = ids.numpy()
+    th.manual_seed(seed + 5)
+    result = agent2.update_net([states, actions, logprobs, rewards, undones, unmasks])
+    th.set_grad_enabled(True)
+    out["update_net.result"] = np.array([float(x) for x in result], dtype=np.float64)
+    dump_net("update_net.after.actor", agent2.act, out)
+    dump_net("update_net.after.critic", agent2.cri, out)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main_a2c():
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    case_a2c("a2c_s3_a1_64x64", 3, 1, (64, 64), horizon_len=96, seed=101, batch_size=32, repeat_times=2)
+    case_a2c("a2c_s8_a2_64x32", 8, 2, (64, 32), horizon_len=80, seed=103, batch_size=16, repeat_times=1, learning_rate=2e-4,
+             clip_grad_norm=0.7)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "a2c"):
+    main_a2c()

@@ -439,7 +439,14 @@ def ppo_minibatch(actor, critic, opt_a, opt_c, batch, hp):
     ratio = np.exp(new_logprob - batch["logprob"])
     adv = batch["advantage"]
     mask_a = unmask if hp.get("mask_actor", True) else np.ones_like(unmask)  # helloworld does not mask the actor terms
-    if hp.get("surrogate", "factor") == "min_clip":  # helloworld_PPO_single_file.py:337-339
+    if hp.get("surrogate", "factor") == "a2c":
+        # AgentA2C.update_objectives (AgentPPO.py:306-311), single-env buffers [H, 1, ...]: new_logprob is summed over the
+        # size-1 env axis, stays [B, A], and obj_actor = mean over [B, A] of adv * logprob = mean_b(adv_b * logp_b) / A
+        inv_a = dt.type(1.0 / mean.shape[1])
+        surrogate = (adv * new_logprob * inv_a).astype(dt)
+        ratio = np.ones_like(adv)
+        d_ratio = (adv * inv_a).astype(dt)                                   # d surrogate / d new_logprob
+    elif hp.get("surrogate", "factor") == "min_clip":  # helloworld_PPO_single_file.py:337-339
         clipped = np.clip(ratio, dt.type(1 - hp["ratio_clip"]), dt.type(1 + hp["ratio_clip"]))
         s1, s2 = adv * ratio, adv * clipped
         take1 = s1 <= s2
@@ -592,6 +599,22 @@ def stats_from_sums(sums, count_all, count_lattice):
     m_lat = sums[1] / count_lattice
     var = (sums[2] - count_lattice * m_lat * m_lat) / (count_lattice - 1.0)
     return mean, math.sqrt(max(var, 0.0))
+
+
+# ------------------------------------------------------------------------------------- A2C variant
+A2C_FLAVOUR = dict(surrogate="a2c", mask_actor=False, lambda_entropy=0.0)
+
+
+def update_net_a2c(actor, critic, opt_a, opt_c, rollout, last_state, ids_per_update, hp):
+    """AgentA2C.update_net / update_objectives -- reference AgentPPO.py:257-311, meaningful for single-env buffers
+    ``[H, 1, ...]`` only (its ``states[indices]`` indexes the time axis alone): same values / GAE /
+    normalisation pass as PPO, then per minibatch the masked-MSE critic step and ``obj_actor = (advantage * new_logprob).mean()``
+    (no ratio, no clip, no entropy term, not masked).  ``ids_per_update`` are time indices.  Returns
+    (obj_critic_avg, obj_actor_avg, 0)."""
+    assert rollout["states"].shape[1] == 1, "A2C of the reference is only coherent for num_envs == 1"
+    hp = dict(hp, **A2C_FLAVOUR)
+    (obj_c, obj_a, _), aux = update_net(actor, critic, opt_a, opt_c, rollout, last_state, ids_per_update, hp)
+    return (obj_c, obj_a, 0.0), aux
 
 
 # ------------------------------------------------------------------------------- helloworld variant

@@ -71,3 +71,4 @@ def discrete_net_of(g, prefix, dtype=np.float32):
     net = net_of(g, prefix, dtype)
     net.pop("action_std_log", None)
     return net
+A2C_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "a2c_*.npz")))

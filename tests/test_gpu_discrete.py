@@ -247,3 +247,33 @@ def test_external_env_rollout_cuda_graph(kind):
         G.assert_close(buf_g2[0], buf_e2[0].cpu().numpy(), 1e-4, 1e-5, "second cycle states")
     result = graphed.update_net(list(graphed.explore_env(env_g, h)))
     assert all(np.isfinite(result))
+
+
+# ------------------------------------------------------------------------------------------------ A2C
+@pytest.mark.parametrize("case", gu.A2C_CASES)
+def test_a2c_update_net_against_reference(case, update_impl):
+    """AgentA2C (reference AgentPPO.py:252-311) on single-env buffers: the B200RL_PPO_A2C actor objective."""
+    from elegantrl_b200 import Config
+    from elegantrl_b200.agents import AgentA2C
+    g = gu.load(case)
+    dims = [int(x) for x in g["dims"]]
+    hp = gu.hyper_of(g)
+    args = Config(AgentA2C, None, {'env_name': 'golden', 'num_envs': 1, 'max_step': 200, 'state_dim': dims[0],
+                                   'action_dim': dims[1], 'if_discrete': False})
+    args.net_dims = dims[4:]
+    for k in ("gamma", "ratio_clip", "lambda_entropy", "clip_grad_norm", "learning_rate", "reward_scale", "batch_size",
+              "repeat_times", "lambda_gae_adv", "if_use_v_trace"):
+        setattr(args, k, hp[k])
+    agent = AgentA2C(args.net_dims, dims[0], dims[1], gpu_id=0, args=args)
+    G.load_module(agent.act, gu.net_of(g, "actor"))
+    G.load_module(agent.cri, gu.net_of(g, "critic"))
+    buffer = [G.cuda(g[f"buf.{k}"]) for k in ("states", "actions", "logprobs", "rewards", "undones", "unmasks")]
+    agent.last_state = G.cuda(g["buf.last_state"])
+    agent._inject_ids = G.cuda(g["update_net.ids"])
+    result = agent.update_net(buffer)
+    G.assert_close(np.array(result), g["update_net.result"], RTOL, 1e-6)
+    assert result[2] == 0.0
+    for which, module in (("actor", agent.act), ("critic", agent.cri)):
+        got, ref = gu.flat_params(G.module_to_net(module)), gu.flat_params(gu.net_of(g, f"update_net.after.{which}"))
+        for a, b in zip(got, ref):
+            G.assert_close(a, b, RTOL, 2e-6, which)

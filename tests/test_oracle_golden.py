@@ -215,3 +215,19 @@ def test_discrete_rollout_cartpole(case):
         np.testing.assert_allclose(out[k], g[f"rollout.{k}"], rtol=1e-4, atol=1e-5, err_msg=k)
     np.testing.assert_allclose(out["last_state"], g["rollout.last_state"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(out["values"], g["gae.values"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", gu.A2C_CASES)
+def test_a2c_update_net(case):
+    """The A2C flavour of the oracle against elegantrl.agents.AgentA2C.update_net on single-env buffers [H, 1, ...]."""
+    g = gu.load(case)
+    hp = gu.hyper_of(g)
+    actor, critic = gu.net_of(g, "actor"), gu.net_of(g, "critic")
+    opt_a, opt_c = po.new_adam_state(actor, True), po.new_adam_state(critic, False)
+    rollout = {k: g[f"buf.{k}"].copy() for k in ("states", "actions", "logprobs", "rewards", "undones", "unmasks")}
+    result, _ = po.update_net_a2c(actor, critic, opt_a, opt_c, rollout, g["buf.last_state"], g["update_net.ids"], hp)
+    np.testing.assert_allclose(result, g["update_net.result"], rtol=1e-4, atol=1e-6)
+    assert result[2] == 0.0 and g["update_net.result"][2] == 0.0
+    for prefix, net in (("actor", actor), ("critic", critic)):
+        for mine, ref in zip(gu.flat_params(net), gu.flat_params(gu.net_of(g, f"update_net.after.{prefix}"))):
+            np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=2e-6)
