@@ -586,3 +586,98 @@ def main_a2c():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "a2c"):
     main_a2c()
+
+
+# --------------------------------------------------------------------------- SAC + ReplayBuffer, oracle groundwork
+def dump_layers(prefix, seq, out):
+    linears = [m for m in seq if isinstance(m, th.nn.Linear)]
+    out[f"{prefix}.n_layers"] = np.int64(len(linears))
+    for i, l in enumerate(linears):
+        out[f"{prefix}.W{i}"] = l.weight.detach().numpy().copy()
+        out[f"{prefix}.b{i}"] = l.bias.detach().numpy().copy()
+
+
+def dump_sac(prefix, agent, out):
+    dump_layers(f"{prefix}.actor.net_s", agent.act.net_s, out)
+    dump_layers(f"{prefix}.actor.net_a", agent.act.net_a, out)
+    for name, cri in (("critic", agent.cri), ("critic_target", agent.cri_target)):
+        dump_layers(f"{prefix}.{name}.encoder", cri.encoder_sa, out)
+        for e, dec in enumerate(cri.decoder_qs):
+            dump_layers(f"{prefix}.{name}.decoder{e}", dec, out)
+    out[f"{prefix}.alpha_log"] = agent.alpha_log.detach().numpy().copy()
+
+
+def case_sac(name, state_dim, action_dim, net_dims, num_seqs, max_size, seed, num_updates=3, **hyper):
+    """ReplayBuffer.update (with wrap-around) / sample and AgentSAC.update_objectives (AgentSAC.py:42-86), minibatch indices
+    and both rsample draws replayed from th.manual_seed."""
+    from elegantrl.agents import AgentSAC as RefAgentSAC
+    from elegantrl.train.replay_buffer import ReplayBuffer as RefReplayBuffer
+    out = {}
+    th.manual_seed(seed)
+    env_args = {'env_name': 'golden', 'num_envs': num_seqs, 'max_step': 200, 'state_dim': state_dim,
+                'action_dim': action_dim, 'if_discrete': False}
+    args = RefConfig(agent_class=RefAgentSAC, env_class=None, env_args=env_args)
+    args.net_dims = list(net_dims)
+    for k, v in hyper.items():
+        setattr(args, k, v)
+    agent = RefAgentSAC(list(net_dims), state_dim, action_dim, gpu_id=-1, args=args)
+    g = th.Generator().manual_seed(seed + 1)
+    with th.no_grad():  # move off the init point; make the target differ from the online critic
+        for p in list(agent.act.parameters()) + list(agent.cri.parameters()):
+            p += 0.05 * th.randn(p.shape, generator=g)
+        for p in agent.cri_target.parameters():
+            p += 0.03 * th.randn(p.shape, generator=g)
+    for k in ("gamma", "clip_grad_norm", "learning_rate", "soft_update_tau", "batch_size", "repeat_times", "reward_scale"):
+        out[f"hp.{k}"] = np.float64(getattr(agent, k))
+    out["hp.target_entropy"] = np.float64(agent.target_entropy)
+    out["hp.num_ensembles"] = np.int64(agent.num_ensembles)
+    out["dims"] = np.array([state_dim, action_dim, num_seqs, max_size] + list(net_dims), dtype=np.int64)
+    dump_sac("init", agent, out)
+
+    # ---- replay buffer: three appends, the last one wraps around
+    buffer = RefReplayBuffer(max_size=max_size, state_dim=state_dim, action_dim=action_dim, gpu_id=-1, num_seqs=num_seqs, args=args)
+    for i, rows in enumerate((max_size // 2, max_size // 3, max_size // 2)):
+        items = (th.randn((rows, num_seqs, state_dim), generator=g), th.rand((rows, num_seqs, action_dim), generator=g) * 2 - 1,
+                 th.randn((rows, num_seqs), generator=g), (th.rand((rows, num_seqs), generator=g) > 0.1).float(),
+                 (th.rand((rows, num_seqs), generator=g) > 0.1).float())
+        for k, t in zip(("states", "actions", "rewards", "undones", "unmasks"), items):
+            out[f"append{i}.{k}"] = t.numpy().copy()
+        buffer.update(items)
+        out[f"append{i}.p"], out[f"append{i}.cur_size"] = np.int64(buffer.p), np.int64(buffer.cur_size)
+    for k in ("states", "actions", "rewards", "undones", "unmasks"):
+        out[f"buffer.{k}"] = getattr(buffer, k).numpy().copy()
+
+    # ---- k updates; RNG consumption per call: randint (sample :121), normal_ (rsample :51), normal_ (rsample :72)
+    b = agent.batch_size
+    th.manual_seed(seed + 5)
+    ids, eps_next, eps_pg = [], [], []
+    for _ in range(num_updates):
+        ids.append(th.randint((buffer.cur_size - 1) * num_seqs, size=(b,)))
+        eps_next.append(th.empty((b, action_dim)).normal_())
+        eps_pg.append(th.empty((b, action_dim)).normal_())
+    out["update.ids"], out["update.eps_next"], out["update.eps_pg"] = (th.stack(x).numpy() for x in (ids, eps_next, eps_pg))
+    th.manual_seed(seed + 5)
+    scalars = []
+    th.set_grad_enabled(True)
+    for u in range(num_updates):
+        scalars.append(agent.update_objectives(buffer, u))
+        assert th.equal(buffer.ids0, th.fmod(ids[u], buffer.cur_size - 1)), "index replay mismatch"
+        if u == 0:
+            dump_sac("after1", agent, out)
+    out["update.scalars"] = np.array(scalars, dtype=np.float64)
+    dump_sac("after", agent, out)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main_sac():
+    th.set_num_threads(1)
+    # BipedalWalker dims of BASELINE config 4 (demo_A2C_PPO.py:212-219 style), small; and a 3-layer / 2-critic variant
+    case_sac("sac_s24_a4_64x32", 24, 4, (64, 32), num_seqs=6, max_size=40, seed=107, batch_size=48, learning_rate=3e-4,
+             soft_update_tau=0.02)
+    case_sac("sac_s3_a1_32x32x16", 3, 1, (32, 32, 16), num_seqs=3, max_size=30, seed=109, batch_size=32, num_ensembles=2,
+             gamma=0.97, clip_grad_norm=0.5)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "sac"):
+    main_sac()
