@@ -9,9 +9,10 @@ The class name contains "PPO" because ``Config.get_if_off_policy`` classifies ag
 (``elegantrl/train/config.py:108-111``).
 
 What runs where
-    explore_env   built-in Pendulum env -> one fused persistent kernel (csrc/rollout.cu), which also produces
-                  V(s_t) and V(last_state); any other vec env -> one policy-step kernel per step
-                  (csrc/forward.cu) around the env's own ``step``
+    explore_env   built-in Pendulum env -> one fused persistent kernel (csrc/rollout_tc.cu: tcgen05; csrc/rollout.cu:
+                  FP32 pipe), which also produces V(s_t) and V(last_state); any other vec env -> one policy-step
+                  kernel per step (csrc/forward.cu) around the env's own ``step``, optionally with the whole loop
+                  captured in a CUDA graph (``cuda_graph_rollout``)
     update_net    values (only if not already produced by the fused rollout) -> GAE reverse scan (csrc/gae.cu)
                   -> ``update_times`` fused minibatch kernels (csrc/update.cu); one D2H copy of 3 floats
 PyTorch here is plumbing only: device memory, streams, ``torch.distributed``.  There is no fallback: without
@@ -192,8 +193,10 @@ class AgentPPO:
 
     def enable_data_parallel(self, group=None):
         """Shard envs over the ranks of a torch.distributed group: each rank rolls out / scans its own env slice;
-        per cycle one all-reduce of the advantage sums, per minibatch one all-reduce of the flat gradient
-        (SURVEY.md section 8(e)).  Replaces the reference's host-pipe trajectory all-gather (run.py:305-320)."""
+        per cycle one all-reduce of the advantage sums, one all-gather of the packed minibatch records and one
+        broadcast of parameters + moments (``sharded_mode = "gather"``, default), or one all-reduce of the flat
+        gradient per minibatch (``"allreduce"``) -- SURVEY.md section 8(e).  Replaces the reference's host-pipe
+        trajectory all-gather (run.py:305-320)."""
         import torch.distributed as dist
         self._dist_group = group if group is not None else dist.group.WORLD
         self._rank, self._world = dist.get_rank(self._dist_group), dist.get_world_size(self._dist_group)
