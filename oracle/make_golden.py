@@ -681,3 +681,72 @@ def main_sac():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "sac"):
     main_sac()
+
+
+def case_sac_cycle(name, num_envs, horizon_len, max_step, max_size, seed, net_dims=(64, 32), **hyper):
+    """One off-policy cycle of the reference: AgentSAC.explore_env (AgentBase.py:130-170) on the torch Pendulum vec env ->
+    ReplayBuffer.update -> AgentSAC.update_net (AgentBase.py:172-189), every random draw replayed."""
+    from elegantrl.agents import AgentSAC as RefAgentSAC
+    from elegantrl.train.replay_buffer import ReplayBuffer as RefReplayBuffer
+    out = {}
+    th.manual_seed(seed)
+    env_args = {'env_name': 'golden', 'num_envs': num_envs, 'max_step': max_step, 'state_dim': 3, 'action_dim': 1, 'if_discrete': False}
+    args = RefConfig(agent_class=RefAgentSAC, env_class=None, env_args=env_args)
+    args.net_dims = list(net_dims)
+    for k, v in hyper.items():
+        setattr(args, k, v)
+    agent = RefAgentSAC(list(net_dims), 3, 1, gpu_id=-1, args=args)
+    for k in ("gamma", "clip_grad_norm", "learning_rate", "soft_update_tau", "batch_size", "repeat_times", "reward_scale"):
+        out[f"hp.{k}"] = np.float64(getattr(agent, k))
+    out["hp.target_entropy"] = np.float64(agent.target_entropy)
+    out["hp.num_ensembles"] = np.int64(agent.num_ensembles)
+    out["dims"] = np.array([3, 1, num_envs, max_size] + list(net_dims), dtype=np.int64)
+    out["horizon_len"], out["max_step"] = np.int64(horizon_len), np.int64(max_step)
+    dump_sac("init", agent, out)
+
+    env = PendulumVecEnv(num_envs=num_envs, gpu_id=-1, max_step=max_step, seed=seed)
+    g = th.Generator().manual_seed(seed + 2)
+    reset_noise = th.rand((horizon_len + 1, num_envs, 2), generator=g)
+    env.inject_reset_noise(reset_noise)
+    state, _ = env.reset()
+    env.cur_step[:] = th.randint(0, max_step, (num_envs,), generator=g, dtype=th.int32)
+    out["env.theta0"], out["env.theta_dot0"], out["env.cur_step0"] = env.theta.numpy().copy(), env.theta_dot.numpy().copy(), env.cur_step.numpy().copy()
+    out["env.reset_noise"] = reset_noise[1:].numpy().copy()
+    agent.last_state = state
+    th.manual_seed(seed + 3)
+    eps = th.stack([th.empty((num_envs, 1)).normal_() for _ in range(horizon_len)])
+    out["explore.eps"] = eps.numpy()
+    th.manual_seed(seed + 3)
+    th.set_grad_enabled(False)
+    items = agent.explore_env(env, horizon_len)
+    for k, t in zip(("states", "actions", "rewards", "undones", "unmasks"), items):
+        out[f"explore.{k}"] = t.numpy().copy()
+    out["explore.last_state"] = agent.last_state.numpy().copy()
+    buffer = RefReplayBuffer(max_size=max_size, state_dim=3, action_dim=1, gpu_id=-1, num_seqs=num_envs, args=args)
+    buffer.update(items)
+    update_times = int(buffer.cur_size * agent.repeat_times / agent.batch_size)
+    b = agent.batch_size
+    th.manual_seed(seed + 5)
+    ids, eps_next, eps_pg = [], [], []
+    for _ in range(update_times):
+        ids.append(th.randint((buffer.cur_size - 1) * num_envs, size=(b,)))
+        eps_next.append(th.empty((b, 1)).normal_())
+        eps_pg.append(th.empty((b, 1)).normal_())
+    out["update.ids"], out["update.eps_next"], out["update.eps_pg"] = (th.stack(x).numpy() for x in (ids, eps_next, eps_pg))
+    th.manual_seed(seed + 5)
+    result = agent.update_net(buffer)
+    th.set_grad_enabled(True)
+    out["update_net.result"] = np.array([float(x) for x in result], dtype=np.float64)
+    dump_sac("after", agent, out)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main_sac_cycle():
+    th.set_num_threads(1)
+    case_sac_cycle("saccycle_pendulum_n12_h24", num_envs=12, horizon_len=24, max_step=9, max_size=64, seed=113,
+                   batch_size=32, repeat_times=4.0, reward_scale=0.5, learning_rate=3e-4)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "saccycle"):
+    main_sac_cycle()

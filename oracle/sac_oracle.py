@@ -228,3 +228,39 @@ def sac_update(agent, batch, eps_next, eps_pg, hp):
     g_a = actor_backward(actor, cache_a, d_tanh, d_logprob)
     _step(actor_params(actor), [g for pair in g_a for g in pair], agent["opt_actor"], hp)
     return float(obj_critic), float(obj_actor)
+
+
+# ------------------------------------------------------------------------------------- rollout + update_net
+def explore_action(actor, state, eps):
+    """ActorSAC.get_action (AgentSAC.py:176-182): tanh(mean + std * eps) -- the tanh'ed action is what the buffer stores."""
+    return actor_forward(actor, state, eps)[0]
+
+
+def explore_pendulum(actor, theta, theta_dot, cur_step, horizon_len, eps, reset_u, reward_scale=1.0, max_step=200):
+    """AgentBase._explore_vec_env, off-policy flavour (AgentBase.py:130-170) on the Pendulum vec env: records
+    (states, actions, rewards * reward_scale, undones, unmasks); no log-probs.  eps [H, N, A], reset_u [H, N, 2]."""
+    from oracle.ppo_oracle import pendulum_observe, pendulum_step
+    dt = theta.dtype
+    n = theta.shape[0]
+    states = np.zeros((horizon_len, n, 3), dt)
+    actions = np.zeros((horizon_len, n, eps.shape[2]), dt)
+    rewards = np.zeros((horizon_len, n), dt)
+    terminals = np.zeros((horizon_len, n), bool)
+    truncates = np.zeros((horizon_len, n), bool)
+    for t in range(horizon_len):
+        state = pendulum_observe(theta, theta_dot)
+        action = explore_action(actor, state, eps[t])
+        states[t], actions[t] = state, action
+        theta, theta_dot, cur_step, reward, terminal, truncate = pendulum_step(theta, theta_dot, cur_step, action[:, 0], reset_u[t], max_step)
+        rewards[t], terminals[t], truncates[t] = reward, terminal, truncate
+    rewards = (rewards * dt.type(reward_scale)).astype(dt)
+    return dict(states=states, actions=actions, rewards=rewards, undones=~terminals, unmasks=~truncates,
+                last_state=pendulum_observe(theta, theta_dot), theta=theta, theta_dot=theta_dot, cur_step=cur_step)
+
+
+def update_net(agent, buffer, ids_per_update, eps_next, eps_pg, hp):
+    """AgentBase.update_net, off-policy (AgentBase.py:172-189): ``int(cur_size * repeat_times / batch_size)`` calls of
+    update_objectives; returns the (nan)means of (obj_critic, obj_actor)."""
+    logs = [sac_update(agent, buffer.sample(ids), eps_next[u], eps_pg[u], hp) for u, ids in enumerate(ids_per_update)]
+    logs = np.array(logs, dtype=np.float64)
+    return float(np.nanmean(logs[:, 0])), float(np.nanmean(logs[:, 1]))

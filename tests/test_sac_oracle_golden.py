@@ -74,3 +74,30 @@ def test_sac_update_objectives(case):
                 np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=2e-6)
     for mine, ref in zip(flat(agent), flat(agent_of(g, "after"))):
         np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=3e-6)
+
+
+SACCYCLE_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(gu.GOLDEN_DIR, "saccycle_*.npz")))
+
+
+@pytest.mark.parametrize("case", SACCYCLE_CASES)
+def test_sac_full_cycle(case):
+    """explore_env (off-policy, tanh'ed actions stored) on the Pendulum vec env -> ReplayBuffer.update -> update_net."""
+    g = gu.load(case)
+    agent = agent_of(g, "init")
+    h, max_step, n, max_size = int(g["horizon_len"]), int(g["max_step"]), int(g["dims"][2]), int(g["dims"][3])
+    hp = {k: float(g[f"hp.{k}"]) for k in ("gamma", "clip_grad_norm", "learning_rate", "soft_update_tau", "target_entropy")}
+    roll = so.explore_pendulum(agent["actor"], g["env.theta0"], g["env.theta_dot0"], g["env.cur_step0"], h, g["explore.eps"],
+                               g["env.reset_noise"], float(g["hp.reward_scale"]), max_step)
+    for k in ("states", "actions", "rewards"):
+        np.testing.assert_allclose(roll[k], g[f"explore.{k}"], rtol=1e-4, atol=1e-5, err_msg=k)
+    assert np.array_equal(roll["undones"], g["explore.undones"]) and np.array_equal(roll["unmasks"], g["explore.unmasks"])
+    assert not g["explore.unmasks"].all()
+    np.testing.assert_allclose(roll["last_state"], g["explore.last_state"], rtol=1e-4, atol=1e-5)
+    buf = so.ReplayBuffer(max_size, 3, 1, n)
+    buf.update(tuple(g[f"explore.{k}"] for k in ("states", "actions", "rewards", "undones", "unmasks")))
+    assert buf.cur_size == h and not buf.if_full
+    assert len(g["update.ids"]) == int(buf.cur_size * float(g["hp.repeat_times"]) / int(g["hp.batch_size"]))
+    result = so.update_net(agent, buf, g["update.ids"], g["update.eps_next"], g["update.eps_pg"], hp)
+    np.testing.assert_allclose(result, g["update_net.result"], rtol=1e-4, atol=2e-6)
+    for mine, ref in zip(flat(agent), flat(agent_of(g, "after"))):
+        np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=3e-6)
