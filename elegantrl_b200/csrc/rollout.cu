@@ -273,8 +273,12 @@ int b200rl_rollout_pendulum(const b200rl_rollout_args* a, void* stream_) {
     const char* mode = getenv("B200RL_ROLLOUT");
     const bool want_ffma = mode && strcmp(mode, "ffma") == 0;
     if (h1 == 64 && h2 == 64 && a->critic && !want_ffma && a->actor->activation == B200RL_ACT_GELU &&
-        a->critic->activation == B200RL_ACT_GELU)
+        a->critic->activation == B200RL_ACT_GELU) {
+#ifdef B200RL_HAVE_TC_WS  // experimental warp-specialised variant (csrc/experimental/, B200RL_BUILD_EXPERIMENTAL=1): opt-in only
+        if (mode && strcmp(mode, "ws") == 0) return b200rl_launch_rollout_tc_ws(P, stream);
+#endif
         return b200rl_launch_rollout_tc(P, stream);
+    }
     if (h1 == 64 && h2 == 64) return launch_rollout<64, 64>(P, stream);
     if (h1 == 128 && h2 == 64) return launch_rollout<128, 64>(P, stream);
     b200rl_set_error("rollout_pendulum: no fused kernel for hidden dims %dx%d (built: 64x64, 128x64); "

@@ -23,3 +23,4 @@ __device__ __forceinline__ float remainder_pos(float a, float b) {
 }
 
 int b200rl_launch_rollout_tc(const RolloutParams& P, cudaStream_t stream);  // rollout_tc.cu
+int b200rl_launch_rollout_tc_ws(const RolloutParams& P, cudaStream_t stream);  // experimental/rollout_tc_ws.cu (optional)
