@@ -291,7 +291,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_ws_kernel(con
 
     if (issuer) {
         // ============================================ issuer warp of this tile: wait for a round, issue, commit -- nothing else
-        const uint32_t d_actor = tmem_base + (uint32_t)(tile * kHid), d_critic = tmem_base + (uint32_t)((kTiles + tile) * kHid);
+        // lane field 0: an M = 128 MMA addresses the whole tile; column = 64 * group (actor groups 0..3, critic groups 4..7)
+        const uint32_t d_actor = (tmem_base & 0x0000FFFFu) + (uint32_t)(tile * kHid);
+        const uint32_t d_critic = (tmem_base & 0x0000FFFFu) + (uint32_t)((kTiles + tile) * kHid);
         const uint32_t a_desc[2] = {(uint32_t)tc05::make_smem_desc(tc05::smem_u32(smem + kOffRing + tile * 2 * kSlotBytes), 256),
                                     (uint32_t)tc05::make_smem_desc(tc05::smem_u32(smem + kOffRing + (kTiles + tile) * 2 * kSlotBytes), 256)};
         uint32_t b_desc[2][2];
