@@ -1,7 +1,7 @@
 """Benchmark of the on-policy hot path: env-steps/sec over full cycles (rollout -> GAE -> PPO update).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's engine, N GPUs of one node
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (PyTorch-CPU port, host cores)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own AgentPPO on the host cores (oracle/_ref)
 
 Workload (BASELINE.json configs[1]): AgentPPO on Pendulum-v1, 65 536 envs PER GPU
 (env-sharded, weak scaling), horizon 128, 2x64 GELU MLP actor + critic, Config defaults batch_size=128,
@@ -51,7 +51,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled every 25 ms DURING the timed region, in-process through NVML
+    """SM clock / power / throttle reasons sampled every 4 ms DURING the timed region, in-process through NVML
     (nvidia_ml_py).  An external `nvidia-smi -lms` loop was measured to stall kernel submission for up to 100 ms per
     query on these hosts, which is as long as the whole timed region; the NVML calls below take microseconds."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
@@ -85,7 +85,7 @@ class ClockSampler:
                 self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, reasons))
             except Exception:  # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.025)
+            self.stop_flag.wait(0.004)
 
     def start(self):
         if self.nv is None:
@@ -108,45 +108,60 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
         reasons = sorted({name for _, _, r in timed for name, bit in self.REASONS if r & bit})
         return {"sm_mhz": statistics.median(c for c, _, _ in timed), "sm_max_mhz": self.sm_max, "reasons": reasons,
-                "samples": len(timed), "power_w_max": max(p for _, p, _ in timed), "how": "NVML in-process, 25 ms period"}
+                "samples": len(timed), "power_w_max": max(p for _, p, _ in timed), "how": "NVML in-process, 4 ms period"}
+
+
+def cpu_backend():
+    """The CPU implementation that is timed as the reference arm / cpu_baseline: the UNMODIFIED reference's own AgentPPO
+    from oracle/_ref (placed by oracle/make_ref.py; travels with the snapshot) -> kind "reference"; only if that copy is
+    absent, the PyTorch-CPU port of its op sequence (oracle/cpu_port.py) -> kind "port"."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        return "reference", ref_runner.time_ref_cycles, "oracle/_ref elegantrl.agents.AgentPPO (unmodified reference, gpu_id=-1)"
+    from oracle.cpu_port import time_cpu_cycles
+    return "port", time_cpu_cycles, "oracle/cpu_port.py (oracle/_ref absent)"
+
+
+def calibrate_threads(time_fn, num_envs=NUM_ENVS):
+    """torch's default of one intra-op thread per logical CPU is several times SLOWER than 8-32 threads on these tiny
+    ops, so the baseline uses the best count -- chosen on FULL-SIZE cycles (the same workload that is then timed), best
+    of 3 per candidate after one warm-up, identically in the engine arm's cpu_baseline leg and in the reference arm."""
+    ncpu = os.cpu_count() or 8
+    candidates = [t for t in (8, 16, 32) if t <= ncpu] or [max(1, ncpu)]
+    scores = {}
+    for t in candidates:
+        r = time_fn(num_envs, HORIZON, NET_DIMS, warmup=1, cycles=3, threads=t, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+        best_cycle = min(e + u for e, u in zip(r["explore_s"], r["update_s"]))
+        scores[t] = num_envs * HORIZON / best_cycle
+    best = max(scores, key=scores.get)
+    return best, scores
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path (oracle/cpu_port.py restates its ATen op sequence) on the host
-    cores, same config / metric; rank 0 only.  Thread count: calibrated (torch's default of one thread per core is
-    several times SLOWER than 8-16 threads on these tiny ops).  Each step is a full cycle at 65 536 envs unless K + W
-    such cycles would not fit in ~3 minutes; then every step is the same cycle on a power-of-two subset of the envs."""
+    """The reference's own CPU implementation of the path (see cpu_backend) on the host cores, same config / metric;
+    rank 0 only.  Each step is a full cycle at 65 536 envs unless K + W such cycles would not fit in ~3 minutes; then
+    every step is the same cycle on a power-of-two subset of the envs (said in cpu_baseline.sample)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch as th
-    from oracle.cpu_port import CpuPPO, best_thread_count
-    from elegantrl_b200.envs import PendulumVecEnv
-    threads, scores = best_thread_count(NET_DIMS, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+    kind, time_fn, what = cpu_backend()
+    threads, scores = calibrate_threads(time_fn)
     budget_s, num_envs = 180.0, NUM_ENVS
     est_full = NUM_ENVS * HORIZON / scores[threads]          # seconds per full cycle, from the calibration run
     while num_envs > 4096 and (args.warmup + args.steps) * est_full * num_envs / NUM_ENVS > budget_s:
         num_envs //= 2
-    th.manual_seed(0)
-    agent = CpuPPO(NET_DIMS, 3, 1, num_envs, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
-    env = PendulumVecEnv(num_envs=num_envs, gpu_id=-1, max_step=200, seed=0)
-    agent.last_state = env.reset()[0]
-    times = []
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        buffer = agent.explore_env(env, HORIZON)
-        agent.update_net(list(buffer))
-        if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    total = sum(times)
-    value = num_envs * HORIZON * len(times) / total
-    sample = (f"{len(times)} cycles of {num_envs} envs x {HORIZON} steps + update after {args.warmup} warm-up; {threads} torch "
-              f"threads chosen by calibration {({t: round(v / 1e6, 2) for t, v in scores.items()})} M env-steps/s")
-    cfg = workload_config(1)
-    cfg["reference_sample_envs"] = num_envs
+    r = time_fn(num_envs, HORIZON, NET_DIMS, warmup=args.warmup, cycles=args.steps, threads=threads,
+                batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+    total = sum(r["explore_s"]) + sum(r["update_s"])
+    value = num_envs * HORIZON * args.steps / total
+    sample = (f"{what}: {args.steps} cycles of {num_envs} envs x {HORIZON} steps + update after {args.warmup} warm-up; {threads} torch "
+              f"threads of {os.cpu_count()} logical CPUs, chosen on full-size cycles (best of 3 per candidate: "
+              f"{({t: round(v / 1e6, 2) for t, v in scores.items()})} M env-steps/s)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "sample_envs": num_envs},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -291,13 +306,15 @@ def run_engine(args):
             "gpu_launches": int(launches), "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_port import best_thread_count, time_cpu_cycles
-        threads, _ = best_thread_count(NET_DIMS, batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
-        cb = time_cpu_cycles(NUM_ENVS, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, threads=threads,
-                             batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
-        line["cpu_baseline"] = {"value": cb["env_steps_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
-                                "sample": f"{cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up, thread count "
-                                          f"calibrated ({cb['threads']} of {os.cpu_count()} logical CPUs); "
+        from oracle.cpu_port import time_cpu_cycles
+        kind, time_fn, what = cpu_backend()
+        threads, scores = calibrate_threads(time_fn)
+        cb = time_fn(NUM_ENVS, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, threads=threads,
+                     batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
+        line["cpu_baseline"] = {"value": cb["env_steps_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": kind,
+                                "sample": f"{what}: {cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up; "
+                                          f"{cb['threads']} torch threads of {os.cpu_count()} logical CPUs, chosen on full-size cycles "
+                                          f"(best of 3 per candidate: {({t: round(v / 1e6, 2) for t, v in scores.items()})} M env-steps/s); "
                                           f"explore {statistics.mean(cb['explore_s']):.3f}s + update {statistics.mean(cb['update_s']):.3f}s per cycle"}
         # the same pinned op sequence as EAGER PyTorch on this very GPU (SURVEY 8(d) "stronger baseline"): what a user of the
         # reference gets with gpu_id=0 -- ~45 launches per env step, ~250 per minibatch.  Informational; ~2 s.

@@ -277,6 +277,7 @@ int b200rl_rollout_pendulum(const b200rl_rollout_args* a, void* stream_) {
 #ifdef B200RL_HAVE_TC_WS  // experimental warp-specialised variant (csrc/experimental/, B200RL_BUILD_EXPERIMENTAL=1): opt-in only
         if (mode && strcmp(mode, "ws") == 0) return b200rl_launch_rollout_tc_ws(P, stream);
 #endif
+        if (mode && strcmp(mode, "ts") == 0) return b200rl_launch_rollout_ts(P, stream);
         return b200rl_launch_rollout_tc(P, stream);
     }
     if (h1 == 64 && h2 == 64) return launch_rollout<64, 64>(P, stream);

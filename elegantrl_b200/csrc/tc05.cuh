@@ -158,3 +158,44 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 }  // namespace tc05
+
+// ------------------------------------------------------------------ additions for the TS (A-in-TMEM) rollout kernel
+namespace tc05 {
+
+// registers -> TMEM, 32 lanes x 16 columns of 32-bit: thread i of the warp writes columns [c, c+16) of TMEM lane
+// (base_lane + i).  Completion: tmem_st_wait() before the data may be consumed by another agent.
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// instruction descriptor, kind::f16 with fp16 A and B, fp32 accumulate, both K-major, dense (cf. cute UMMA::InstrDescriptor)
+__device__ __host__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4)                     // c_format = F32
+           | (0u << 7) | (0u << 10)      // a_format = b_format = F16
+           | ((uint32_t)(N >> 3) << 17)  // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16 (M x N x 16): A = 8 TMEM columns (two fp16 K-elements per 32-bit cell,
+// lane = row) starting at tmem_a; B = K-major shared-memory descriptor.  Issued by ONE thread.
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// {hi half: fp16(a), lo half: fp16(b)}, round to nearest even
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+}  // namespace tc05

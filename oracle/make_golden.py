@@ -303,6 +303,21 @@ if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "elegant
     main()
 
 
+def main_large_rollout():
+    """One rollout golden that spans a whole persistent CTA of the tcgen05 kernels (448 envs = 3.5 tiles of 128 rows)
+    three times over: N = 1 344 = 3 CTAs incl. their half tiles, H = 40 (the horizon of the small golden: Pendulum
+    amplifies rounding differences chaotically beyond that), truncations staggered over the envs."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    case_rollout("rollout_pendulum_n1344_h40", num_envs=1344, horizon_len=40, max_step=25, seed=71,
+                 batch_size=64, repeat_times=4, reward_scale=0.5)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "large"):
+    main_large_rollout()
+
+
 # --------------------------------------------------------------------------- helloworld variant (BASELINE configs[0])
 def import_helloworld():
     """Import the reference's helloworld/helloworld_PPO_single_file.py with a stub `gymnasium` (absent here; the

@@ -9,7 +9,7 @@ from tests import golden_utils as gu
 from tests.gpu_utils import load_module
 
 CASE_SEEDS = {"synth_s3_a1_64x64": 11, "synth_s8_a2_128x64": 23, "synth_s5_a3_64x48x32": 37, "synth_s3_a1_n1": 41,
-              "rollout_pendulum_n32_h40": 53, "rollout_pendulum_n8_h16": 61}
+              "rollout_pendulum_n32_h40": 53, "rollout_pendulum_n8_h16": 61, "rollout_pendulum_n1344_h40": 71}
 
 
 def port_from_golden(g):

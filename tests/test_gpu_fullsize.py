@@ -32,7 +32,7 @@ def make(seed=0):
     return agent, env
 
 
-@pytest.fixture(params=["tc", "ffma"])
+@pytest.fixture(params=["ts", "tc", "ffma"])
 def rollout_impl(request, monkeypatch):
     monkeypatch.setenv("B200RL_ROLLOUT", request.param)
     return request.param
@@ -96,10 +96,11 @@ def test_full_size_rollout_is_deterministic(rollout_impl):
 
 def test_both_rollout_kernels_agree_at_full_size(monkeypatch):
     res = {}
-    for mode in ("tc", "ffma"):
+    for mode in ("tc", "ts", "ffma"):
         monkeypatch.setenv("B200RL_ROLLOUT", mode)
         agent, env = make(seed=5)
         buf = agent.explore_env(env, 16)
         res[mode] = [t.float().cpu().numpy() for t in buf] + [agent._value_cache[1].cpu().numpy()]
-    for a, b in zip(res["tc"], res["ffma"]):
-        np.testing.assert_allclose(a, b, rtol=1e-4, atol=2e-5)
+    for other in ("tc", "ts"):
+        for a, b in zip(res[other], res["ffma"]):
+            np.testing.assert_allclose(a, b, rtol=1e-4, atol=2e-5)

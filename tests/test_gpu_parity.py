@@ -293,9 +293,10 @@ def test_update_device_sampled_indices():
 
 
 # ---------------------------------------------------------------------------------------- rollout
-@pytest.fixture(params=["tc", "ffma"])
+@pytest.fixture(params=["ts", "tc", "ffma"])
 def rollout_impl(request, monkeypatch):
-    """Both fused-rollout implementations (tcgen05 / TMEM and FP32-pipe) must agree with the reference."""
+    """All fused-rollout implementations (tcgen05 with the A operand in tensor memory, tcgen05 with a shared-memory
+    ring, FP32 pipe) must agree with the reference."""
     monkeypatch.setenv("B200RL_ROLLOUT", request.param)
     return request.param
 
