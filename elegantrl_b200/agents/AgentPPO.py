@@ -19,6 +19,7 @@ PyTorch here is plumbing only: device memory, streams, ``torch.distributed``.  T
 ``libb200rl.so`` or without a CUDA device the agent raises.
 """
 import ctypes as C
+import functools
 import os
 from typing import Optional, Tuple
 
@@ -30,6 +31,20 @@ from .. import _lib
 from .nets import ActorDiscretePPO, ActorPPO, CriticPPO
 
 TEN = th.Tensor
+
+
+def _on_device(method):
+    """Run an engine entry point with ``self.device`` as the CURRENT CUDA device: the C-ABI launches on the stream handle it
+    is given (the default stream's handle is 0 = "the current device's"), and ``cudaGetDevice`` / SM-count queries inside
+    the library read the current device.  The reference's learners construct agents with ``gpu_id = k`` without ever
+    calling ``set_device`` (``elegantrl/train/run.py:237``)."""
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        if self.device.type != "cuda" or th.cuda.current_device() == self.device.index:
+            return method(self, *args, **kwargs)
+        with th.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapped
 
 
 def _linears(module: nn.Module):
@@ -106,6 +121,7 @@ class AgentPPO:
         self._policy_steps = 0       # Philox offset of the per-step policy kernel (external envs)
         self._workspace: Optional[TEN] = None
         self._value_cache = None     # (key, values [H, N], last_value [N]) produced by the fused rollout
+        self._rollout_id = 0         # generation counter of fused rollouts (part of the value-cache key)
         self._dist_group = None      # set by enable_data_parallel()
         self._rank, self._world = 0, 1
         self.last_update_info = {}
@@ -202,6 +218,7 @@ class AgentPPO:
         self._rank, self._world = dist.get_rank(self._dist_group), dist.get_world_size(self._dist_group)
 
     # ------------------------------------------------------------------------------------- rollout
+    @_on_device
     def explore_env(self, env, horizon_len: int) -> Tuple[TEN, TEN, TEN, TEN, TEN, TEN]:
         """Reference AgentBase.explore_env dispatch (AgentBase.py:70-74) + AgentPPO._explore_vec_env /
         _explore_one_env (AgentPPO.py:34-129).  Returns (states, actions, logprobs, rewards, undones, unmasks)."""
@@ -245,17 +262,24 @@ class AgentPPO:
         _lib.check(lib.b200rl_rollout_pendulum(C.byref(args), self._stream()), "rollout_pendulum")
         env.global_step += h
         self.last_state = last_state
+        self._rollout_id += 1
+        states._b200rl_rollout_id = self._rollout_id   # the tag travels with THIS tensor object (a recycled address cannot alias it)
         self._value_cache = (self._cache_key(states), values, last_value)
         return states, actions, logprobs, rewards, undones, unmasks
 
     def _cache_key(self, states: TEN):
-        return states.data_ptr(), tuple(states.shape), id(self.cri), self.cri.net[0].weight.data_ptr()
+        """Identity of (this very rollout's states tensor, this very critic state): the rollout generation tag set on the
+        tensor object, and the in-place version counter of every critic tensor (``load_state_dict``, an optimizer step or
+        the engine's own update -- which bumps them explicitly -- invalidate the cached values)."""
+        versions = tuple(p._version for p in self.cri.parameters()) + tuple(b._version for b in self.cri.buffers())
+        return getattr(states, "_b200rl_rollout_id", None), tuple(states.shape), id(self.cri), versions
 
     def explore_action(self, state: TEN) -> Tuple[TEN, TEN]:
         """ActorPPO.get_action through the engine (reference AgentPPO.py:131-133): (action, logprob)."""
         action, logprob, _ = self._policy_step(state)
         return action, logprob
 
+    @_on_device
     def _policy_step(self, state: TEN, eps: Optional[TEN] = None):
         """One engine exploration step: (action [rows, A] pre-tanh, logprob [rows], env_action = tanh(action));
         categorical policy: (action int32 [rows], logprob [rows], env_action = action.long())."""
@@ -378,8 +402,9 @@ class AgentPPO:
         terminals = th.zeros((h, 1), dtype=th.bool)
         truncates = th.zeros((h, 1), dtype=th.bool)
         state = self.last_state.to(dev)
+        noise = getattr(self, "_inject_eps", None)  # parity tests: [H, 1, A]
         for t in range(h):
-            action, logprob, env_action = self._policy_step(state)
+            action, logprob, env_action = self._policy_step(state, None if noise is None else noise[t].contiguous())
             states[t], actions[t], logprobs[t] = state, action, logprob
             ary_state, reward, terminal, truncate, _ = env.step(env_action[0].cpu().numpy())
             if terminal or truncate:
@@ -392,6 +417,7 @@ class AgentPPO:
                 th.logical_not(terminals).to(dev), th.logical_not(truncates).to(dev))
 
     # -------------------------------------------------------------------------------------- update
+    @_on_device
     def get_values(self, states: TEN) -> TEN:
         """critic(states) for [..., S] -> [...] (reference update_net values pass, AgentPPO.py:141-143)."""
         lib = self._require_engine()
@@ -402,6 +428,7 @@ class AgentPPO:
                    "mlp_forward")
         return out.reshape(states.shape[:-1])
 
+    @_on_device
     def get_advantages(self, states: TEN, rewards: TEN, undones: TEN, unmasks: TEN, values: TEN,
                        last_value: Optional[TEN] = None):
         """Reference AgentPPO.get_advantages (AgentPPO.py:207-232); mutates rewards / undones in place like it.
@@ -427,6 +454,7 @@ class AgentPPO:
         obj_critic, obj_actor, obj_entropy = self.update_net_device(buffer).tolist()  # the one D2H copy of the cycle
         return obj_critic, obj_actor, obj_entropy
 
+    @_on_device
     def update_net_device(self, buffer) -> TEN:
         """``update_net`` without the host synchronisation: the three scalars stay in a device tensor."""
         lib = self._require_engine()
@@ -480,6 +508,9 @@ class AgentPPO:
         else:
             self._update_sharded(lib, act_desc, cri_desc, act_adam, cri_adam, tb, hp, update_times, ids, out, workspace)
         self._update_draws += update_times
+        # the kernels wrote the parameters behind autograd's back: bump the in-place version counters (value-cache key,
+        # and anything else of torch's that watches them)
+        th.autograd.graph.increment_version(list(self.act.parameters()) + list(self.cri.parameters()))
         self._set_adam_step(self.act_optimizer, self.act, act_adam.step)
         self._set_adam_step(self.cri_optimizer, self.cri, cri_adam.step)
         self.last_update_info = dict(update_times=update_times, advantages=advantages, reward_sums=reward_sums,

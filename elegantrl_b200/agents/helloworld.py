@@ -23,6 +23,8 @@ update_net returns                        (objC, objA_surrogate, ent)   (objC, o
 """
 from typing import Tuple
 
+import copy
+
 import numpy as np
 import torch as th
 
@@ -38,6 +40,7 @@ class AgentPPO(_EngineAgentPPO):
             from ..config import Config
             args = Config()
             args.learning_rate, args.lambda_entropy = 6e-5, 0.01
+        args = copy.copy(args)  # the overrides below must not leak into a Config the caller reuses (evaluator, other agents)
         for name, value in (("activation", "relu"), ("use_state_norm", False), ("clip_grad_norm", 0.0), ("num_envs", 1),
                             ("if_discrete", False)):
             setattr(args, name, value)

@@ -400,11 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
 }  // namespace
 
 int b200rl_launch_rollout_tc(const RolloutParams& P, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        B200RL_CHECK_CUDA(cudaFuncSetAttribute(rollout_pendulum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
-    }
+    // per-device attribute: set on every launch (a process may drive more than one GPU)
+    B200RL_CHECK_CUDA(cudaFuncSetAttribute(rollout_pendulum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const int grid = (P.N + kRowsPerCta - 1) / kRowsPerCta;
     rollout_pendulum_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(P);
     B200RL_COUNT_LAUNCH(1);

@@ -1,4 +1,4 @@
-from .pendulum import PendulumVecEnv
+from .pendulum import PendulumEnv, PendulumVecEnv
 from .cartpole import CartPoleVecEnv
 
-__all__ = ["PendulumVecEnv", "CartPoleVecEnv"]
+__all__ = ["PendulumEnv", "PendulumVecEnv", "CartPoleVecEnv"]

@@ -117,3 +117,26 @@ class PendulumVecEnv:
         self.theta_dot = self.theta_dot.contiguous()
         self.cur_step = self.cur_step.contiguous()
         return self.theta, self.theta_dot, self.cur_step
+
+
+class PendulumEnv:
+    """ONE pendulum with the gym-style numpy contract of the reference's single-env path (what ``AgentPPO._explore_one_env``
+    calls, reference ``elegantrl/agents/AgentPPO.py:63-70``; ``envs/CustomGymEnv.py:24-44``): ``reset() -> (state [S]
+    ndarray, info)``, ``step(action [A] ndarray) -> (state, reward float, terminal bool, truncate bool, info)``, NO
+    auto-reset -- the caller resets after a terminal / truncated step.  Same physics as ``PendulumVecEnv`` (it wraps one
+    with ``num_envs = 1`` on the CPU; the vec env's internal auto-reset is undone by the caller's ``reset()``)."""
+
+    def __init__(self, max_step: int = 200, seed: int = 0, **_kwargs):
+        self.inner = PendulumVecEnv(num_envs=1, gpu_id=-1, max_step=max_step, seed=seed)
+        self.env_name, self.num_envs, self.max_step = "Pendulum-v1", 1, int(max_step)
+        self.state_dim, self.action_dim, self.if_discrete = 3, 1, False
+
+    def reset(self, **_kwargs):
+        return self.inner.reset()[0][0].numpy().copy(), dict()
+
+    def step(self, action):
+        state, reward, terminal, truncate, _ = self.inner.step(th.as_tensor(action, dtype=th.float32).reshape(1, 1))
+        return state[0].numpy().copy(), float(reward[0]), bool(terminal[0]), bool(truncate[0]), dict()
+
+    def close(self):
+        pass

@@ -765,3 +765,62 @@ def main_sac_cycle():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "saccycle"):
     main_sac_cycle()
+
+
+# ------------------------------------------------------------------ single-env rollout
+def case_one_env(name, horizon_len, max_step, seed, net_dims=(64, 64), **hyper):
+    """Reference AgentPPO._explore_one_env (elegantrl/agents/AgentPPO.py:34-85) with ``num_envs = 1`` on the numpy
+    gym-style ``elegantrl_b200.envs.PendulumEnv``: numpy action out / numpy state in per step, ``env.reset()`` by the
+    agent after a truncated step, outputs reshaped to [H, 1, ...].  Policy noise replayed from ``th.manual_seed``,
+    the env's reset noise injected (the same rows are handed to the env of the drop-in agent in the parity test)."""
+    from elegantrl_b200.envs import PendulumEnv
+    out = {}
+    agent = make_ref_agent(3, 1, net_dims, 1, seed, **hyper)
+    assert not agent.if_vec_env
+    perturb_nets(agent, seed + 1, std_log=-0.5, norm_stats=True)
+    record_hyper(agent, out)
+    out["dims"] = np.array([3, 1, 1, horizon_len] + list(net_dims), dtype=np.int64)
+    out["max_step"] = np.int64(max_step)
+    dump_net("actor", agent.act, out)
+    dump_net("critic", agent.cri, out)
+
+    env = PendulumEnv(max_step=max_step, seed=seed)
+    g = th.Generator().manual_seed(seed + 2)
+    reset_noise = th.rand((2 * horizon_len + 2, 1, 2), generator=g)   # a truncated step consumes two rows (step + reset)
+    out["env.reset_noise"] = reset_noise.numpy().copy()
+    env.inner.inject_reset_noise(reset_noise)
+    state, _ = env.reset()
+    out["state0"] = np.asarray(state, dtype=np.float32).copy()
+    agent.last_state = th.as_tensor(state, dtype=th.float32).unsqueeze(0)
+
+    th.manual_seed(seed + 3)
+    eps = th.stack([th.randn((1, 1)) for _ in range(horizon_len)])
+    out["eps"] = eps.numpy()
+    th.manual_seed(seed + 3)
+    with th.no_grad():
+        states, actions, logprobs, rewards, undones, unmasks = agent.explore_env(env, horizon_len)
+    with th.no_grad():
+        mean0 = agent.act.net(agent.act.state_norm(states[0]))
+    assert th.equal(actions[0], mean0 + agent.act.action_std_log.exp() * eps[0]), "noise replay mismatch"
+    assert tuple(states.shape) == (horizon_len, 1, 3) and int((~unmasks).sum()) >= 2
+    for k, t in zip(("states", "actions", "logprobs", "rewards", "undones", "unmasks"),
+                    (states, actions, logprobs, rewards, undones, unmasks)):
+        out[f"rollout.{k}"] = t.numpy().copy()
+    out["rollout.last_state"] = agent.last_state.numpy().copy()
+    buf = (states, actions, logprobs, rewards, undones, unmasks, agent.last_state.clone())
+    record_gae(agent, buf, out, "gae")
+    record_update_net(agent, buf, out, seed + 5)
+    np.savez_compressed(os.path.join(OUT_DIR, f"{name}.npz"), **out)
+    print(f"| wrote {name}.npz  ({len(out)} arrays)")
+
+
+def main_one_env():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    case_one_env("oneenv_pendulum_h48", horizon_len=48, max_step=13, seed=83, batch_size=16, repeat_times=2,
+                 reward_scale=0.5)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "oneenv"):
+    main_one_env()
