@@ -36,14 +36,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "b200rl.h"))
-    experimental = os.environ.get("B200RL_BUILD_EXPERIMENTAL") == "1"
-    obj_dir = os.path.join(HERE, "build_experimental" if experimental else "build")  # different flags: separate objects
+    obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
     extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("B200RL_EXTRA_NVCC_FLAGS", "").split()
     sources = list(SOURCES)
-    if experimental:  # kernels written but not yet validated on a GPU: opt-in only (then always relink)
-        sources.append(os.path.join("experimental", "rollout_tc_ws.cu"))
-        extra.append("-DB200RL_HAVE_TC_WS")
 
     def compile_one(src):
         src_path = os.path.join(CSRC, src)
@@ -59,17 +55,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
         objs = list(pool.map(compile_one, sources))
-    marker = os.path.join(HERE, "build", ".flavour")
-    flavour = "experimental" if experimental else "default"
-    previous = open(marker).read() if os.path.exists(marker) else ""
-    if force or previous != flavour or _stale(LIB_PATH, objs):
+    if force or _stale(LIB_PATH, objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-        os.makedirs(os.path.dirname(marker), exist_ok=True)
-        with open(marker, "w") as f:
-            f.write(flavour)
     return LIB_PATH
 
 

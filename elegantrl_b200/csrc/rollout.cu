@@ -268,17 +268,15 @@ int b200rl_rollout_pendulum(const b200rl_rollout_args* a, void* stream_) {
     P.last_value = a->last_value; P.eps = a->eps; P.reset_noise = a->reset_noise;
     P.seed = a->seed; P.step_offset = a->step_offset; P.env_offset = a->env_offset;
 
-    // 2x64 GELU actor + critic (BASELINE config 2): tcgen05 / TMEM kernel unless B200RL_ROLLOUT=ffma asks for the
-    // FP32-pipe kernel (kept as the cross-check and for the other shapes)
+    // 2x64 GELU actor + critic (BASELINE config 2): the tcgen05 kernel with the layer-2 A operand in tensor memory
+    // (rollout_ts.cu).  B200RL_ROLLOUT=tc selects the earlier tcgen05 kernel with the shared-memory operand ring
+    // (rollout_tc.cu), =ffma the FP32-pipe kernel below -- both kept as independent cross-checks (the tests run all three).
     const char* mode = getenv("B200RL_ROLLOUT");
     const bool want_ffma = mode && strcmp(mode, "ffma") == 0;
     if (h1 == 64 && h2 == 64 && a->critic && !want_ffma && a->actor->activation == B200RL_ACT_GELU &&
         a->critic->activation == B200RL_ACT_GELU) {
-#ifdef B200RL_HAVE_TC_WS  // experimental warp-specialised variant (csrc/experimental/, B200RL_BUILD_EXPERIMENTAL=1): opt-in only
-        if (mode && strcmp(mode, "ws") == 0) return b200rl_launch_rollout_tc_ws(P, stream);
-#endif
-        if (mode && strcmp(mode, "ts") == 0) return b200rl_launch_rollout_ts(P, stream);
-        return b200rl_launch_rollout_tc(P, stream);
+        if (mode && strcmp(mode, "tc") == 0) return b200rl_launch_rollout_tc(P, stream);
+        return b200rl_launch_rollout_ts(P, stream);
     }
     if (h1 == 64 && h2 == 64) return launch_rollout<64, 64>(P, stream);
     if (h1 == 128 && h2 == 64) return launch_rollout<128, 64>(P, stream);

@@ -24,4 +24,3 @@ __device__ __forceinline__ float remainder_pos(float a, float b) {
 
 int b200rl_launch_rollout_tc(const RolloutParams& P, cudaStream_t stream);  // rollout_tc.cu
 int b200rl_launch_rollout_ts(const RolloutParams& P, cudaStream_t stream);  // rollout_ts.cu (A operand in tensor memory)
-int b200rl_launch_rollout_tc_ws(const RolloutParams& P, cudaStream_t stream);  // experimental/rollout_tc_ws.cu (optional)
