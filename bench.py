@@ -205,21 +205,17 @@ def run_engine(args):
         buffer = agent.explore_env(env, HORIZON)
         return agent.update_net_device(list(buffer))
 
-    # pinned host mirrors for the end-to-end arm: env state in, last_state + 3 scalars out
-    host_in = [th.empty(NUM_ENVS, dtype=dt).pin_memory() for dt in (th.float32, th.float32, th.int32)]
+    # pinned host mirrors for the end-to-end arm: the env state block [3, N] in, last_state + env state + 3 scalars out
+    host_in = th.empty((3, NUM_ENVS), dtype=th.float32).pin_memory()
     host_last_state = th.empty((NUM_ENVS, 3), dtype=th.float32).pin_memory()
-    for h, d in zip(host_in, env.engine_state()):
-        h.copy_(d)
+    host_in.copy_(env.engine_state_block())
 
     def cycle_e2e():
-        theta, theta_dot, cur_step = env.engine_state()
-        theta.copy_(host_in[0], non_blocking=True)          # H2D: the step's inputs from pinned host memory
-        theta_dot.copy_(host_in[1], non_blocking=True)
-        cur_step.copy_(host_in[2], non_blocking=True)
+        block = env.engine_state_block()
+        block.copy_(host_in, non_blocking=True)              # H2D: the step's inputs from pinned host memory
         buffer = agent.explore_env(env, HORIZON)             # public API
         host_last_state.copy_(agent.last_state, non_blocking=True)   # D2H: final once the rollout is done (stream order)
-        for h, d in zip(host_in, env.engine_state()):        # D2H: env state for the host-side loop
-            h.copy_(d, non_blocking=True)
+        host_in.copy_(block, non_blocking=True)              # D2H: env state for the host-side loop
         result = agent.update_net(list(buffer))              # public API: returns 3 Python floats (D2H + sync)
         return result
 

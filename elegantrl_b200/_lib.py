@@ -47,6 +47,14 @@ class TrainBuffer(C.Structure):
                 ("horizon_len", C.c_int32), ("num_envs", C.c_int32), ("discrete_actions", C.c_int32), ("reserved", C.c_int32)]
 
 
+MAX_PEERS, PX_FLAGS = 8, 64
+
+
+class PeerExchange(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("data", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS),
+                ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class RolloutArgs(C.Structure):
     _fields_ = [("actor", C.POINTER(Net)), ("critic", C.POINTER(Net)),
                 ("num_envs", C.c_int32), ("horizon_len", C.c_int32), ("max_step", C.c_int32),
@@ -89,6 +97,13 @@ SIGNATURES = {
     "b200rl_ppo_apply": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.POINTER(Adam), C.POINTER(Adam),
                                    C.POINTER(PPOHyper), C.c_void_p, C.c_int64, C.c_void_p]),
     "b200rl_loss_means": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200rl_workspace_error_offset": (C.c_int64, []),
+    "b200rl_update_tc_supported": (C.c_int32, [C.POINTER(Net), C.POINTER(Net), C.POINTER(PPOHyper)]),
+    "b200rl_peer_exchange_floats": (C.c_int64, [C.POINTER(Net), C.POINTER(Net)]),
+    "b200rl_ppo_update_sharded": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.POINTER(Adam), C.POINTER(Adam),
+                                            C.POINTER(TrainBuffer), C.POINTER(PPOHyper), C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.POINTER(PeerExchange), C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

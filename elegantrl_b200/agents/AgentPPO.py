@@ -122,7 +122,12 @@ class AgentPPO:
         self._workspace: Optional[TEN] = None
         self._value_cache = None     # (key, values [H, N], last_value [N]) produced by the fused rollout
         self._rollout_id = 0         # generation counter of fused rollouts (part of the value-cache key)
+        self._lib_handle = None      # ctypes handle (not pickled: see __getstate__)
+        self._fused_pre = None       # ((n, h), output tensors) allocated ahead for the next fused rollout
+        self._rollout_args = None    # reused b200rl_rollout_args block
+        self._desc_cache = {}        # id(module) -> (parameter pointers, descriptor)
         self._dist_group = None      # set by enable_data_parallel()
+        self._px = None
         self._rank, self._world = 0, 1
         self.last_update_info = {}
         self.cuda_graph_rollout = bool(getattr(args, "cuda_graph_rollout", False))  # external envs: see _explore_vec_env_graphed
@@ -131,6 +136,13 @@ class AgentPPO:
         self._full_std = False       # advantage std over the whole buffer instead of the [::4, ::4] lattice
 
     # ------------------------------------------------------------------------------------ plumbing
+    def __getstate__(self):
+        """The agent may be pickled (multiprocessing): raw handles, pointer blocks and CUDA graphs are per process."""
+        state = dict(self.__dict__)
+        state.update(_lib_handle=None, _fused_pre=None, _rollout_args=None, _desc_cache={}, _rollout_graphs={},
+                     _workspace=None, _value_cache=None, _px=None, _dist_group=None)
+        return state
+
     def _require_engine(self):
         if self.device.type != "cuda":
             raise _lib.B200RLError("AgentPPO (B200 engine) needs a CUDA device; there is no CPU path "
@@ -143,7 +155,18 @@ class AgentPPO:
         return t
 
     def _net_desc(self, module: nn.Module) -> _lib.Net:
-        """C descriptor aliasing the module's parameter storages (rebuilt per call: cheap, always current)."""
+        """C descriptor aliasing the module's parameter storages; cached per module and revalidated on every call by the
+        storages' addresses (``load_state_dict`` keeps them, ``.to()`` / re-assignment does not), the activation name and the
+        presence of the normalisation statistics."""
+        ptrs = tuple(p.data_ptr() for p in module.parameters()) + tuple(b.data_ptr() for b in module.buffers())
+        hit = self._desc_cache.get(id(module))
+        if hit is not None and hit[0] == ptrs and hit[2] is module:
+            return hit[1]
+        net = self._build_net_desc(module)
+        self._desc_cache[id(module)] = (ptrs, net, module)
+        return net
+
+    def _build_net_desc(self, module: nn.Module) -> _lib.Net:
         linears = _linears(module)
         assert 1 <= len(linears) <= _lib.MAX_LINEAR, "too many layers for the engine"
         net = _lib.Net()
@@ -216,6 +239,51 @@ class AgentPPO:
         import torch.distributed as dist
         self._dist_group = group if group is not None else dist.group.WORLD
         self._rank, self._world = dist.get_rank(self._dist_group), dist.get_world_size(self._dist_group)
+        self._px = None  # peer-memory exchange (sharded_mode "peer"): allocated at the first sharded update
+
+    def _peer_exchange(self, lib, act_desc, cri_desc):
+        """Symmetric (peer-mapped) exchange buffer + flag array of the in-kernel gradient all-reduce
+        (``b200rl_ppo_update_sharded``).  torch's symmetric-memory allocator is the plumbing: it allocates the same buffer
+        on every rank of the group and maps every peer's copy into this process (NVLink P2P)."""
+        if self._px is not None:
+            return self._px[0]
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        floats = int(lib.b200rl_peer_exchange_floats(C.byref(act_desc), C.byref(cri_desc)))
+        data = symm.empty(floats, dtype=th.float32, device=self.device)
+        flags = symm.empty(_lib.PX_FLAGS, dtype=th.int32, device=self.device)
+        hd, hf = symm.rendezvous(data, self._dist_group), symm.rendezvous(flags, self._dist_group)
+        data.zero_()
+        flags.zero_()
+        th.cuda.synchronize(self.device)
+        dist.barrier(group=self._dist_group)   # every rank's flags are zero before anybody raises one
+        px = _lib.PeerExchange(rank=self._rank, world=self._world, epoch=0)
+        for r in range(self._world):
+            px.data[r], px.flags[r] = int(hd.buffer_ptrs[r]), int(hf.buffer_ptrs[r])
+        self._px = (px, data, flags, hd, hf)
+        return px
+
+    def _peer_mode(self, lib, act_desc, cri_desc, hp) -> bool:
+        """Use the in-kernel exchange?  ``sharded_mode``: "peer" (required), "auto" (default: peer when the nets have the
+        tcgen05 kernel's shape and symmetric memory can be set up, else "gather"), "gather", "allreduce"."""
+        mode = getattr(self, "sharded_mode", "auto")
+        if mode not in ("auto", "peer"):
+            return False
+        ok = (bool(lib.b200rl_update_tc_supported(C.byref(act_desc), C.byref(cri_desc), C.byref(hp)))
+              and self.batch_size % self._world == 0 and self.batch_size // self._world <= 128 and self._world <= _lib.MAX_PEERS)
+        if ok and self._px is None:
+            try:
+                self._peer_exchange(lib, act_desc, cri_desc)
+            except Exception as err:  # noqa: BLE001
+                if mode == "peer":
+                    raise
+                import warnings
+                warnings.warn(f"AgentPPO: peer-memory exchange unavailable ({err!r}); using the NCCL all-gather mode")
+                self.sharded_mode = "gather"
+                return False
+        if not ok and mode == "peer":
+            raise _lib.B200RLError("sharded_mode='peer' needs S -> 64 -> 64 -> OUT GELU nets and batch_size / world <= 128")
+        return ok
 
     # ------------------------------------------------------------------------------------- rollout
     @_on_device
@@ -235,36 +303,48 @@ class AgentPPO:
         return (env.device == self.device and self.state_dim == 3 and self.action_dim == 1
                 and tuple(self.net_dims) in ((64, 64), (128, 64)) and env.num_envs == self.num_envs)
 
+    def _fused_outputs(self, n: int, h: int):
+        dev, f32 = self.device, th.float32
+        return (th.empty((h, n, 3), dtype=f32, device=dev), th.empty((h, n, 1), dtype=f32, device=dev),
+                th.empty((h, n), dtype=f32, device=dev), th.empty((h, n), dtype=f32, device=dev),
+                th.empty((h, n), dtype=th.bool, device=dev), th.empty((h, n), dtype=th.bool, device=dev),
+                th.empty((h, n), dtype=f32, device=dev), th.empty((n, 3), dtype=f32, device=dev),
+                th.empty((n,), dtype=f32, device=dev))
+
     def _explore_fused_pendulum(self, env, horizon_len: int):
-        lib = _lib.load()
-        n, h, dev = env.num_envs, int(horizon_len), self.device
+        """One launch.  The host work between the caller's last synchronisation and this launch is the end-to-end
+        critical path (the GPU idles meanwhile), so it is kept minimal: the nine output tensors of THIS call were
+        allocated at the end of the previous call (while the GPU was busy), the net descriptors are cached, the
+        argument block is reused."""
+        lib = self._lib_handle
+        if lib is None:
+            lib = self._lib_handle = _lib.load()
+        n, h = env.num_envs, int(horizon_len)
+        pre, self._fused_pre = self._fused_pre, None
+        outs = pre[1] if (pre is not None and pre[0] == (n, h)) else self._fused_outputs(n, h)
+        states, actions, logprobs, rewards, undones, unmasks, values, last_state, last_value = outs
         theta, theta_dot, cur_step = env.engine_state()
-        states = th.empty((h, n, 3), dtype=th.float32, device=dev)
-        actions = th.empty((h, n, 1), dtype=th.float32, device=dev)
-        logprobs = th.empty((h, n), dtype=th.float32, device=dev)
-        rewards = th.empty((h, n), dtype=th.float32, device=dev)
-        undones = th.empty((h, n), dtype=th.bool, device=dev)
-        unmasks = th.empty((h, n), dtype=th.bool, device=dev)
-        values = th.empty((h, n), dtype=th.float32, device=dev)
-        last_state = th.empty((n, 3), dtype=th.float32, device=dev)
-        last_value = th.empty((n,), dtype=th.float32, device=dev)
         act_desc, cri_desc = self._net_desc(self.act), self._net_desc(self.cri)
         eps = getattr(self, "_inject_eps", None)
         reset_noise = getattr(self, "_inject_reset_noise", None)
-        args = _lib.RolloutArgs(
-            actor=C.pointer(act_desc), critic=C.pointer(cri_desc), num_envs=n, horizon_len=h, max_step=env.max_step,
-            reward_scale=float(self.reward_scale), theta=_lib.ptr(theta), theta_dot=_lib.ptr(theta_dot),
-            cur_step=_lib.ptr(cur_step), states=_lib.ptr(states), actions=_lib.ptr(actions), logprobs=_lib.ptr(logprobs),
-            rewards=_lib.ptr(rewards), undones=_lib.ptr(undones), unmasks=_lib.ptr(unmasks), values=_lib.ptr(values),
-            last_state=_lib.ptr(last_state), last_value=_lib.ptr(last_value), eps=_lib.ptr(eps),
-            reset_noise=_lib.ptr(reset_noise), seed=self.seed, step_offset=env.global_step,
-            env_offset=self._rank * n)
+        args = self._rollout_args
+        if args is None:
+            args = self._rollout_args = _lib.RolloutArgs()
+        args.actor, args.critic = C.pointer(act_desc), C.pointer(cri_desc)
+        args.num_envs, args.horizon_len, args.max_step, args.reward_scale = n, h, env.max_step, float(self.reward_scale)
+        args.theta, args.theta_dot, args.cur_step = theta.data_ptr(), theta_dot.data_ptr(), cur_step.data_ptr()
+        args.states, args.actions, args.logprobs, args.rewards = states.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), rewards.data_ptr()
+        args.undones, args.unmasks, args.values = undones.data_ptr(), unmasks.data_ptr(), values.data_ptr()
+        args.last_state, args.last_value = last_state.data_ptr(), last_value.data_ptr()
+        args.eps, args.reset_noise = _lib.ptr(eps), _lib.ptr(reset_noise)
+        args.seed, args.step_offset, args.env_offset = self.seed, env.global_step, self._rank * n
         _lib.check(lib.b200rl_rollout_pendulum(C.byref(args), self._stream()), "rollout_pendulum")
         env.global_step += h
         self.last_state = last_state
         self._rollout_id += 1
         states._b200rl_rollout_id = self._rollout_id   # the tag travels with THIS tensor object (a recycled address cannot alias it)
         self._value_cache = (self._cache_key(states), values, last_value)
+        self._fused_pre = ((n, h), self._fused_outputs(n, h))   # the next call's outputs, allocated while the GPU is busy
         return states, actions, logprobs, rewards, undones, unmasks
 
     def _cache_key(self, states: TEN):
@@ -452,6 +532,10 @@ class AgentPPO:
         """Reference AgentPPO.update_net (AgentPPO.py:135-171): returns (obj_critic, obj_actor, obj_entropy)
         averaged over ``update_times = int(H * repeat_times / batch_size)`` minibatch updates."""
         obj_critic, obj_actor, obj_entropy = self.update_net_device(buffer).tolist()  # the one D2H copy of the cycle
+        if obj_critic != obj_critic and getattr(self, "_px", None) is not None:   # NaN: did a peer fail to answer?
+            off = int(_lib.load().b200rl_workspace_error_offset())
+            if int(self._workspace[off:off + 4].view(th.int32).item()) != 0:
+                raise _lib.B200RLError("env-sharded update: a peer rank did not join the gradient exchange within 2 s")
         return obj_critic, obj_actor, obj_entropy
 
     @_on_device
@@ -479,25 +563,26 @@ class AgentPPO:
         advantages, reward_sums, stat_sums = self.get_advantages(states, rewards, undones, unmasks, values, last_value)
 
         n_global = n * self._world
-        if self._world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(stat_sums, group=self._dist_group)
-        stats = th.empty(4, dtype=th.float32, device=dev)
         count_lattice = 0 if self._full_std else ((h + 3) // 4) * ((n_global + 3) // 4)
-        _lib.check(lib.b200rl_adv_stats(_lib.ptr(stat_sums), h * n_global, count_lattice, _lib.ptr(stats), self._stream()),
-                   "adv_stats")
-
         update_times = int(h * self.repeat_times / self.batch_size)
         assert update_times >= 1
         act_desc, cri_desc = self._net_desc(self.act), self._net_desc(self.cri)
         act_adam, cri_adam = self._adam_desc(self.act_optimizer, self.act), self._adam_desc(self.cri_optimizer, self.cri)
         workspace = self._get_workspace(act_desc, cri_desc)
+        hp = _lib.PPOHyper(ratio_clip=float(self.ratio_clip), lambda_entropy=float(self.lambda_entropy),
+                           clip_grad_norm=float(self.clip_grad_norm or 0.0), flags=int(self._ppo_flags))
+        stats = th.empty(4, dtype=th.float32, device=dev)
+        peer = self._world > 1 and self._peer_mode(lib, act_desc, cri_desc, hp)
+        if not peer:
+            if self._world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(stat_sums, group=self._dist_group)
+            _lib.check(lib.b200rl_adv_stats(_lib.ptr(stat_sums), h * n_global, count_lattice, _lib.ptr(stats), self._stream()),
+                       "adv_stats")
         tb = _lib.TrainBuffer(states=_lib.ptr(states), actions=_lib.ptr(actions), unmasks=_lib.ptr(unmasks),
                               logprobs=_lib.ptr(self._check(logprobs, "logprobs")), advantages=_lib.ptr(advantages),
                               reward_sums=_lib.ptr(reward_sums), adv_stats=_lib.ptr(stats), horizon_len=h, num_envs=n,
                               discrete_actions=int(self._categorical))
-        hp = _lib.PPOHyper(ratio_clip=float(self.ratio_clip), lambda_entropy=float(self.lambda_entropy),
-                           clip_grad_norm=float(self.clip_grad_norm or 0.0), flags=int(self._ppo_flags))
         out = th.empty(3, dtype=th.float32, device=dev)
         ids = getattr(self, "_inject_ids", None)
         if self._world == 1:
@@ -505,6 +590,16 @@ class AgentPPO:
                                              C.byref(tb), C.byref(hp), self.batch_size, update_times, _lib.ptr(ids),
                                              self.seed, self._update_draws, _lib.ptr(out), _lib.ptr(workspace),
                                              workspace.numel(), self._stream()), "ppo_update")
+        elif peer:
+            # zero host-issued collectives: statistics and gradients are exchanged inside the update kernel (NVLink)
+            px = self._px[0]
+            seed = self.seed + 0x9E3779B9 * (self._rank + 1)  # independent index streams per shard
+            _lib.check(lib.b200rl_ppo_update_sharded(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam),
+                                                     C.byref(tb), C.byref(hp), self.batch_size, update_times, _lib.ptr(ids), seed,
+                                                     self._update_draws, _lib.ptr(stat_sums), h * n_global, count_lattice,
+                                                     _lib.ptr(stats), _lib.ptr(out), _lib.ptr(workspace), workspace.numel(),
+                                                     C.byref(px), self._stream()), "ppo_update_sharded")
+            px.epoch += update_times
         else:
             self._update_sharded(lib, act_desc, cri_desc, act_adam, cri_adam, tb, hp, update_times, ids, out, workspace)
         self._update_draws += update_times

@@ -14,6 +14,7 @@ struct RolloutParams {
     const float* eps; const float* reset_noise;
     uint64_t seed, step_offset;
     int64_t env_offset;
+    int rows_per_cta;   // rollout_ts.cu: envs per persistent CTA (set by its launcher)
 };
 
 // th.remainder(a, b) for b > 0 (exact: fmod then sign fix, as ATen)

@@ -25,6 +25,8 @@
 //            critic chunks -> env step, trajectory stores, x~(t+1), arrive bar_x (the next step's layer 1 overlaps the
 //            critic head) -> wait d2 -> head -> value.
 // Every barrier completes exactly once per evaluation, so all parities are (evaluation counter & 1).
+#include <stdlib.h>
+
 #include "rollout_params.cuh"
 #include "ts_mlp.cuh"
 
@@ -33,7 +35,15 @@ namespace {
 using namespace tsmlp;
 
 constexpr int kTiles = 4, kRowsPerCta = 448;
-constexpr int kWorkerWarps = 14, kIssuerWarps = kTiles, kWarps = kWorkerWarps + kIssuerWarps, kThreads = kWarps * 32;
+constexpr int kWorkerWarps = 14, kIssuerWarps = kTiles;
+// Variant bits (B200RL_TS_VARIANT, measured in profiles/r02_*_ts_variants.log):
+//   1  software-pipelined tensor-memory loads (the load of chunk c + 1 is in flight while chunk c is evaluated)
+//   2  issuer warps on the two schedulers that host only 3 worker warps (warp ids 14, 15, 18, 19; 16 and 17 stay idle)
+//   4  one arrival per 32 hidden units instead of per 16 (half the arrivals / issuer wake-ups; 8 UMMAs per wake-up)
+//   8  the state row of step t is stored while the actor's last UMMAs run (it is known at the start of the step)
+constexpr int kDefaultVariant = 0;
+constexpr int kVarPrefetch = 1, kVarIssuerPlace = 2, kVarArrive2 = 4, kVarEarlyStore = 8;
+template <int V> constexpr int warps_of() { return (V & kVarIssuerPlace) ? 20 : kWorkerWarps + kIssuerWarps; }
 constexpr int kTileCols = 128;   // TMEM columns per tile: X [0, 64) + D [64, 128)
 
 // ---- dynamic shared memory map (bytes)
@@ -65,7 +75,7 @@ DEV NetImage net_image(int net) {
 }
 
 DEV void load_small(const b200rl_net& net, float* sm) {
-    for (int i = threadIdx.x; i < kHid; i += kThreads) sm[kW3 + i] = net.weight[2][i];
+    for (int i = threadIdx.x; i < kHid; i += blockDim.x) sm[kW3 + i] = net.weight[2][i];
     if (threadIdx.x == 0) sm[kB3] = net.bias[2][0];
     if (threadIdx.x < 3) {
         sm[kAvg + threadIdx.x] = net.state_avg ? net.state_avg[threadIdx.x] : 0.0f;
@@ -73,24 +83,30 @@ DEV void load_small(const b200rl_net& net, float* sm) {
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const __grid_constant__ RolloutParams P) {
+template <int V>
+__global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_kernel(const __grid_constant__ RolloutParams P) {
+    constexpr bool kPrefetch = (V & kVarPrefetch) != 0, kArrive2 = (V & kVarArrive2) != 0, kEarly = (V & kVarEarlyStore) != 0;
+    constexpr int kThreads = warps_of<V>() * 32;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* small = reinterpret_cast<float*>(smem + kOffSmall);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = P.N, H = P.H;
+    const int rows_cta = P.rows_per_cta;          // envs of this CTA: a multiple of 32 (whole warps), <= 448
+    const int warps_cta = rows_cta >> 5;
 
     // ---- one-time setup: TMEM, mbarriers, operand images
     if (warp == 0) tc05::tmem_alloc<512>(tmem_slot);
     if (threadIdx.x == 32) {
         for (int t = 0; t < kTiles; ++t) {
-            const uint32_t arrivals = t == 3 ? 2u : 4u;   // one elected lane per worker warp of the tile
+            const int w = warps_cta - 4 * t;              // worker warps of the tile
+            const uint32_t arrivals = w >= 4 ? 4u : (w > 0 ? (uint32_t)w : 1u);   // one elected lane per worker warp of the tile
             uint64_t* b = bars + t * kBarsPerTile;
             tc05::mbar_init(&b[0], arrivals);              // bar_x
             tc05::mbar_init(&b[1], 1);                     // d1 (tcgen05.commit)
             tc05::mbar_init(&b[2], 1);                     // d2
-            for (int c = 0; c < 4; ++c) tc05::mbar_init(&b[3 + c], arrivals);
+            for (int c = 0; c < 4; ++c) tc05::mbar_init(&b[3 + c], arrivals);   // variant 4 uses the first two
         }
         tc05::mbar_fence_init();
     }
@@ -107,47 +123,57 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
     tc05::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    // issuer warp of tile i: warp 14 + i, or (variant 2) warps 14, 15, 18, 19 -- ids 2, 3 (mod 4), the schedulers with 3 workers
+    int issuer_tile = -1;
+    if (warp >= kWorkerWarps) {
+        if (V & kVarIssuerPlace) issuer_tile = (warp & 2) ? ((warp - kWorkerWarps) >> 2) * 2 + (warp & 1) : -1;
+        else issuer_tile = warp - kWorkerWarps;
+    }
     if (warp >= kWorkerWarps) {
         // ======================================================================== issuer warp of one tile
-        const int tile = warp - kWorkerWarps;
-        const bool tile_used = blockIdx.x * kRowsPerCta + tile * kTileRows < N;
+        const int tile = issuer_tile;
+        const bool tile_used = tile >= 0 && tile * kTileRows < rows_cta && blockIdx.x * rows_cta + tile * kTileRows < N;
         if (tile_used) {
             uint64_t* b = bars + tile * kBarsPerTile;
             const uint32_t tX = tmem_base + (uint32_t)(tile * kTileCols), tD = tX + kHid;
-            const NetDescs nd[2] = {make_descs(smem, net_image(0)), make_descs(smem, net_image(1))};
+            const NetDescs nd_a = make_descs(smem, net_image(0)), nd_c = make_descs(smem, net_image(1));
             const uint64_t ac_desc = tc05::make_smem_desc(tc05::smem_u32(smem + kOffAc), kSboK8);
-            const uint64_t a1_desc[2] = {tc05::make_smem_desc(tc05::smem_u32(smem + kOffA1 + (tile * 2 + 0) * kA1Bytes), kSboK8),
-                                         tc05::make_smem_desc(tc05::smem_u32(smem + kOffA1 + (tile * 2 + 1) * kA1Bytes), kSboK8)};
+            const uint64_t a1_a = tc05::make_smem_desc(tc05::smem_u32(smem + kOffA1 + (tile * 2 + 0) * kA1Bytes), kSboK8);
+            const uint64_t a1_c = tc05::make_smem_desc(tc05::smem_u32(smem + kOffA1 + (tile * 2 + 1) * kA1Bytes), kSboK8);
             uint32_t ph = 0;
-            for (int t = 0; t <= H; ++t) {
-                tc05::mbar_wait(&b[0], t & 1);             // x~(t) of both nets is in shared memory
-                for (int net = (t == H ? 1 : 0); net < 2; ++net) {
+            auto evaluate = [&](const NetDescs& nd, uint64_t a1_desc) {
+                tc05::fence_after_thread_sync();
+                if (tc05::elect_one()) {
+                    issue_layer1(tX, a1_desc, nd);
+                    tc05::mma_commit(&b[1]);
+                }
+                __syncwarp();
+                constexpr int kArrivals = kArrive2 ? 2 : 4;
+#pragma unroll 1
+                for (int c = 0; c < kArrivals; ++c) {
+                    tc05::mbar_wait(&b[3 + c], ph & 1);
                     tc05::fence_after_thread_sync();
                     if (tc05::elect_one()) {
-                        issue_layer1(tX, a1_desc[net], nd[net]);
-                        tc05::mma_commit(&b[1]);
+                        if (c == 0) issue_bias(tD, ac_desc, nd);   // D is free: every worker read it before arriving
+                        if (kArrive2) { issue_layer2_chunk(tD, tX, nd, 2 * c); issue_layer2_chunk(tD, tX, nd, 2 * c + 1); }
+                        else issue_layer2_chunk(tD, tX, nd, c);
+                        if (c == kArrivals - 1) tc05::mma_commit(&b[2]);
                     }
                     __syncwarp();
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        tc05::mbar_wait(&b[3 + c], ph & 1);
-                        tc05::fence_after_thread_sync();
-                        if (tc05::elect_one()) {
-                            if (c == 0) issue_bias(tD, ac_desc, nd[net]);   // D is free: every worker read it before arriving
-                            issue_layer2_chunk(tD, tX, nd[net], c);
-                            if (c == 3) tc05::mma_commit(&b[2]);
-                        }
-                        __syncwarp();
-                    }
-                    ph += 1;
                 }
+                ph += 1;
+            };
+            for (int t = 0; t <= H; ++t) {
+                tc05::mbar_wait(&b[0], t & 1);             // x~(t) of both nets is in shared memory
+                if (t < H) evaluate(nd_a, a1_a);
+                evaluate(nd_c, a1_c);
             }
         }
     } else {
         // =================================================================== worker warp: thread = one env
         const int tile = warp >> 2, quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int n = blockIdx.x * kRowsPerCta + tile * kTileRows + row;
+        const int n = blockIdx.x * rows_cta + tile * kTileRows + row;
         const int n_warp0 = n - lane;
         const bool live = n < N;
         const bool warp_used = n_warp0 < N;    // a warp without envs must still not deadlock its tile: see below
@@ -163,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
         // the tile's barriers expect one arrival per worker warp of the tile that holds envs of the CTA's LAST tile too: a
         // partially filled tile (ragged N) keeps all its warps running on dead rows (finite garbage, never stored)
         (void)warp_used;
-        const bool tile_used = blockIdx.x * kRowsPerCta + tile * kTileRows < N;
+        const bool tile_used = warp < warps_cta && blockIdx.x * rows_cta + tile * kTileRows < N;
         if (tile_used) {
             float theta = live ? P.theta[n] : 0.0f, theta_dot = live ? P.theta_dot[n] : 0.0f;
             int cur_step = live ? P.cur_step[n] : 0;
@@ -182,14 +208,51 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(&b[0]);
             };
+            auto chunk_done = [&](int c) {   // the converted columns of chunk c (and, variant 4, c - 1) may be consumed
+                if (kArrive2 && !(c & 1)) return;
+                tc05::tmem_st_wait();
+                tc05::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(&b[3 + (kArrive2 ? (c >> 1) : c)]);
+            };
             auto hidden = [&]() {   // this row's 64 hidden units: fp32 -> GELU -> fp16 pairs in place, 16 at a time
+                if (kPrefetch) {
+                    float va[16], vb[16];
+                    tc05::tmem_ld_32x32b_x16(tX, va);
+                    tmem_ld_wait_tied(va);
+                    tc05::tmem_ld_32x32b_x16(tX + 16, vb);
+                    hidden_chunk_from_regs<true>(tX, va);
+                    chunk_done(0);
+                    tmem_ld_wait_tied(vb);
+                    tc05::tmem_ld_32x32b_x16(tX + 32, va);
+                    hidden_chunk_from_regs<true>(tX + 16, vb);
+                    chunk_done(1);
+                    tmem_ld_wait_tied(va);
+                    tc05::tmem_ld_32x32b_x16(tX + 48, vb);
+                    hidden_chunk_from_regs<true>(tX + 32, va);
+                    chunk_done(2);
+                    tmem_ld_wait_tied(vb);
+                    hidden_chunk_from_regs<true>(tX + 48, vb);
+                    chunk_done(3);
+                } else {
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    hidden_chunk_inplace<true>(tX + 16 * c);
-                    tc05::tmem_st_wait();
-                    tc05::fence_before_thread_sync();
+                    for (int c = 0; c < 4; ++c) {
+                        hidden_chunk_inplace<true>(tX + 16 * c);
+                        chunk_done(c);
+                    }
+                }
+            };
+            auto head = [&](const float* sm) {
+                return kPrefetch ? head_dot_pipelined<true>(tD, sm + kW3, sm[kB3]) : head_dot<true>(tD, sm + kW3, sm[kB3]);
+            };
+            auto store_state_row = [&](float* dst_states, float o0, float o1, float o2) {   // staged -> 128-bit stores
+                if (vec_ok) {
+                    my_stage[lane * 3 + 0] = o0; my_stage[lane * 3 + 1] = o1; my_stage[lane * 3 + 2] = o2;
                     __syncwarp();
-                    if (lane == 0) tc05::mbar_arrive(&b[3 + c]);
+                    if (lane < 24) reinterpret_cast<float4*>(dst_states + (size_t)n_warp0 * 3)[lane] = *reinterpret_cast<const float4*>(my_stage + 4 * lane);
+                    __syncwarp();
+                } else if (live) {
+                    dst_states[(size_t)n * 3 + 0] = o0; dst_states[(size_t)n * 3 + 1] = o1; dst_states[(size_t)n * 3 + 2] = o2;
                 }
             };
 
@@ -215,9 +278,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
                     }
                     if (P.eps && live) e = P.eps[rowbase + n];
                     if (P.reset_noise && live) reset_u = make_float2(P.reset_noise[(rowbase + n) * 2], P.reset_noise[(rowbase + n) * 2 + 1]);
+                    if (kEarly) store_state_row(P.states + (size_t)t * N * 3, obs0, obs1, obs2);
                     tc05::mbar_wait(&b[2], ph & 1);
                     tc05::fence_after_thread_sync();
-                    const float mu = head_dot<true>(tD, sm_a + kW3, sm_a[kB3]);
+                    const float mu = head(sm_a);
                     tc05::fence_before_thread_sync();   // D reads are ordered before this thread's next arrival (critic chunk 0)
                     ph += 1;
                     action = __fadd_rn(__fmul_rn(e, sd), mu);
@@ -228,18 +292,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
                 tc05::mbar_wait(&b[1], ph & 1);
                 tc05::fence_after_thread_sync();
                 hidden();
-                // state row of step t (or last_state): staged through shared memory -> 128-bit stores
-                {
-                    float* dst_states = last ? P.last_state : P.states + (size_t)t * N * 3;
-                    if (vec_ok) {
-                        my_stage[lane * 3 + 0] = obs0; my_stage[lane * 3 + 1] = obs1; my_stage[lane * 3 + 2] = obs2;
-                        __syncwarp();
-                        if (lane < 24) reinterpret_cast<float4*>(dst_states + (size_t)n_warp0 * 3)[lane] = *reinterpret_cast<const float4*>(my_stage + 4 * lane);
-                        __syncwarp();
-                    } else if (live) {
-                        dst_states[(size_t)n * 3 + 0] = obs0; dst_states[(size_t)n * 3 + 1] = obs1; dst_states[(size_t)n * 3 + 2] = obs2;
-                    }
-                }
+                // state row of step t (or last_state)
+                if (!kEarly || last) store_state_row(last ? P.last_state : P.states + (size_t)t * N * 3, obs0, obs1, obs2);
                 if (!last) {
                     // env.step(tanh(action))  -- same op sequence as rollout.cu / envs/pendulum.py
                     const float torque = fminf(fmaxf(__fmul_rn(tanhf(action), 2.0f), -2.0f), 2.0f);
@@ -281,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
                 }
                 tc05::mbar_wait(&b[2], ph & 1);
                 tc05::fence_after_thread_sync();
-                const float val = head_dot<true>(tD, sm_c + kW3, sm_c[kB3]);
+                const float val = head(sm_c);
                 tc05::fence_before_thread_sync();
                 ph += 1;
                 if (live) {
@@ -300,11 +354,45 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_ts_kernel(const 
 
 }  // namespace
 
-int b200rl_launch_rollout_ts(const RolloutParams& P, cudaStream_t stream) {
-    B200RL_CHECK_CUDA(cudaFuncSetAttribute(rollout_pendulum_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    const int grid = (P.N + kRowsPerCta - 1) / kRowsPerCta;
-    rollout_pendulum_ts_kernel<<<grid, kThreads, kSmemBytes, stream>>>(P);
+template <int V>
+static int launch_variant(const RolloutParams& P, cudaStream_t stream) {
+    B200RL_CHECK_CUDA(cudaFuncSetAttribute(rollout_pendulum_ts_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const int grid = (P.N + P.rows_per_cta - 1) / P.rows_per_cta;
+    rollout_pendulum_ts_kernel<V><<<grid, warps_of<V>() * 32, kSmemBytes, stream>>>(P);
     B200RL_COUNT_LAUNCH(1);
     B200RL_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Envs per CTA: the fewest whole warps that still cover N with one CTA per SM (148 SMs; 448 = 3.5 tiles at 65 536 envs).
+// Small shards (an 8-GPU split of 65 536 envs, BASELINE configs[2]'s 2 048 envs per GPU) get short CTAs on MANY SMs
+// instead of a few full ones: the kernel's time is the per-CTA step latency times H, which shrinks with the rows.
+static int rows_per_cta_for(int N) {
+    const char* o = getenv("B200RL_TS_ROWS");
+    int rows = o ? atoi(o) : ((N + 147) / 148 + 31) / 32 * 32;
+    rows = rows < 32 ? 32 : (rows > kRowsPerCta ? kRowsPerCta : rows);
+    return rows / 32 * 32;
+}
+
+int b200rl_launch_rollout_ts(const RolloutParams& P_in, cudaStream_t stream) {
+    RolloutParams P = P_in;
+    P.rows_per_cta = rows_per_cta_for(P.N);
+    const char* v = getenv("B200RL_TS_VARIANT");
+    switch (v ? atoi(v) : kDefaultVariant) {
+        case 0: return launch_variant<0>(P, stream);
+        case 1: return launch_variant<1>(P, stream);
+        case 2: return launch_variant<2>(P, stream);
+        case 3: return launch_variant<3>(P, stream);
+        case 4: return launch_variant<4>(P, stream);
+        case 5: return launch_variant<5>(P, stream);
+        case 7: return launch_variant<7>(P, stream);
+        case 8: return launch_variant<8>(P, stream);
+        case 9: return launch_variant<9>(P, stream);
+        case 11: return launch_variant<11>(P, stream);
+        case 13: return launch_variant<13>(P, stream);
+        case 15: return launch_variant<15>(P, stream);
+        default: break;
+    }
+    b200rl_set_error("rollout_ts: B200RL_TS_VARIANT=%s is not built", v);
+    return 3;
 }

@@ -199,3 +199,43 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 }
 
 }  // namespace tc05
+
+// ------------------------------------------------- additions for the tcgen05 PPO update kernel (update_tc.cu)
+namespace tc05 {
+
+// general shared-memory matrix descriptor, no swizzle: `lbo_bytes` / `sbo_bytes` as the canonical layouts define them
+//   K-major  ((8,m),(T,2k)):((1T,SBO),(1,LBO))   SBO = stride between 8-row groups, LBO = stride between 16-byte K chunks
+//   MN-major ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)) SBO = stride between 16-byte MN groups, LBO = stride between 8-deep K groups
+// (cute/atom/mma_traits_sm100.hpp, make_umma_desc).  An image written K-major for X [rows][K] is at the same time the MN-major
+// image of X^T with the two strides swapped -- that is how the backward pass reads nn.Linear weights transposed in place.
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::tf32 instruction descriptor with the operand majors: bit 15 = A is MN-major, bit 16 = B is MN-major
+__device__ __host__ constexpr uint32_t make_idesc_tf32_ex(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return make_idesc_tf32(M, N) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16);
+}
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32 (M x N x 8): A = 8 TMEM columns of fp32 (lane = row) starting at tmem_a
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace tc05

@@ -1,0 +1,152 @@
+// Building blocks of the tcgen05 PPO update (update_tc.cu) and its unit test (tools/tc_train_test.cu): forward AND backward
+// of a  S -> 64 -> 64 -> OUT  GELU MLP on a tile of 128 sampled transitions, thread = sample = TMEM lane.
+// Reference arithmetic: AgentPPO.update_objectives (elegantrl/agents/AgentPPO.py:173-205) through build_mlp's
+// Linear-GELU-Linear-GELU-Linear (elegantrl/agents/AgentBase.py:345-365); fp32 parity via 3xTF32 (hi/lo planes of both
+// operands, three UMMAs per K step: hi*hi + lo*hi + hi*lo).
+//
+// Operand images (no swizzle; tc05::make_smem_desc_ex):
+//   * "K-major image" of a weight W [R][K] exactly as nn.Linear stores it: offset(r, k) = (r/8)*(K/4)*128 + (k/4)*128 + (r%8)*16
+//     + (k%4)*4.  Forward reads it K-major (B = W, D = A W^T); the backward data gradient reads THE SAME bytes as the MN-major
+//     operand W^T (D = dZ W) by swapping the two strides of the descriptor -- no transposed copy.
+//   * "row-written image" of a per-sample matrix Q [128 samples][C]: offset(b, c) = (c/4)*2048 + b*16 + (c%4)*4, i.e. sample b
+//     stores its own row with 128-bit stores (a warp covers 512 contiguous bytes per 4-column group: conflict-free).  Read as
+//     an MN-major operand with MN = column, K = sample: this is how the weight gradients  dW = dZ^T X  (a contraction over
+//     the SAMPLE axis) reach the tensor core without any transposition through shared memory.
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace tctrain {
+
+constexpr int kHid = 64, kTile = 128;
+constexpr int kWPlaneBytes = kHid * kHid * 4;        // one tf32 plane of a 64 x 64 weight, K-major image: 16 KB
+constexpr int kGAPlaneBytes = kHid * kTile * 4;      // row-written image [128][64]: 32 KB
+constexpr int kGB2PlaneBytes = 72 * kTile * 4;       // row-written image [128][64 + 8]: 36 KB
+constexpr uint32_t kRowGroupStride = kTile * 16;     // bytes between 4-column groups of a row-written image
+
+// ---- exact-erf GELU and its derivative from ONE evaluation of q = Phi(-|x|) (tools/fit_gelu.py; max abs error 5.8e-7 / 1e-6)
+//   GELU(x) = max(x, 0) - |x| q,   GELU'(x) = Phi(x) + x phi(x),  Phi(x) = x >= 0 ? 1 - q : q,  phi(x) = exp(-x^2/2) / sqrt(2 pi)
+DEV void gelu_and_grad(float x, float& g, float& dg) {
+    constexpr float L = 6.2225397f;
+    const float zn = fmaxf(-fabsf(x), -L);
+    float p = fmaf(1.775934289e-05f, zn, 6.477866232e-04f);
+    p = fmaf(p, zn, 7.724114180e-03f);
+    p = fmaf(p, zn, 5.292681266e-02f);
+    p = fmaf(p, zn, -4.590827042e-01f);
+    p = fmaf(p, zn, 1.151116861e+00f);
+    const float q = tc05::ex2_approx(fmaf(p, zn, -1.0f));
+    g = fmaf(zn, q, fmaxf(x, 0.0f));
+    const float pdf = tc05::ex2_approx(zn * zn * -0.72134752044f) * kInvSqrt2Pi;   // exp(-x^2/2); the clamp only matters where it is 0
+    dg = fmaf(x, pdf, x >= 0.0f ? 1.0f - q : q);
+}
+
+DEV float gelu_only(float x) {
+    constexpr float L = 6.2225397f;
+    const float zn = fmaxf(-fabsf(x), -L);
+    float p = fmaf(1.775934289e-05f, zn, 6.477866232e-04f);
+    p = fmaf(p, zn, 7.724114180e-03f);
+    p = fmaf(p, zn, 5.292681266e-02f);
+    p = fmaf(p, zn, -4.590827042e-01f);
+    p = fmaf(p, zn, 1.151116861e+00f);
+    return fmaf(zn, tc05::ex2_approx(fmaf(p, zn, -1.0f)), fmaxf(x, 0.0f));
+}
+// Sum over the 32 lanes of a warp of 16 per-lane values with 16 shuffles (recursive halving: every step exchanges half of
+// the values a lane still holds): afterwards lane l holds the total of value index (l >> 1) & 15 (lanes l and l ^ 1 the same).
+DEV float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int s = 8, mask = 16; s >= 1; s >>= 1, mask >>= 1) {
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = upper ? v[i] : v[i + s];
+            const float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ---- staging
+// nn.Linear weight [64][64] (read L2-coherently: Adam rewrites it between minibatches) -> hi / lo K-major images
+DEV void stage_w_planes(const float* W, unsigned char* hi, unsigned char* lo, int tid, int nthreads) {
+    for (int i = tid; i < kHid * kHid; i += nthreads) {
+        const int n = i >> 6, k = i & 63;
+        const float w = __ldcg(W + i), h = tc05::tf32_hi(w);
+        const uint32_t off = tc05::operand_offset(n, k, kHid);
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = w - h;
+    }
+}
+// 16 consecutive columns of this thread's row -> hi / lo planes in tensor memory (two tcgen05.st; caller waits)
+DEV void store_hi_lo_tmem(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float hi = tc05::tf32_hi(v[i]);
+        h[i] = __float_as_uint(hi);
+        l[i] = __float_as_uint(v[i] - hi);
+    }
+    tc05::tmem_st_32x32b_x16(taddr_hi, h);
+    tc05::tmem_st_32x32b_x16(taddr_lo, l);
+}
+DEV void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// NV consecutive columns [col0, col0 + NV) (col0 % 4 == 0) of sample b's row -> hi / lo row-written images
+template <int NV>
+DEV void store_hi_lo_rows_n(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[NV]) {
+    const uint32_t hi0 = tc05::smem_u32(hi_plane) + (uint32_t)(col0 >> 2) * kRowGroupStride + (uint32_t)b * 16;
+    const uint32_t lo0 = tc05::smem_u32(lo_plane) + (uint32_t)(col0 >> 2) * kRowGroupStride + (uint32_t)b * 16;
+#pragma unroll
+    for (int q = 0; q < NV / 4; ++q) {
+        const float h0 = tc05::tf32_hi(v[4 * q]), h1 = tc05::tf32_hi(v[4 * q + 1]), h2 = tc05::tf32_hi(v[4 * q + 2]), h3 = tc05::tf32_hi(v[4 * q + 3]);
+        st_shared_v4(hi0 + q * kRowGroupStride, h0, h1, h2, h3);
+        st_shared_v4(lo0 + q * kRowGroupStride, v[4 * q] - h0, v[4 * q + 1] - h1, v[4 * q + 2] - h2, v[4 * q + 3] - h3);
+    }
+}
+DEV void store_hi_lo_rows(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[16]) {
+    store_hi_lo_rows_n<16>(hi_plane, lo_plane, b, col0, v);
+}
+DEV void store_hi_lo_rows8(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[8]) {
+    store_hi_lo_rows_n<8>(hi_plane, lo_plane, b, col0, v);
+}
+
+// ---- issuer side (ONE thread)
+// D[128 x 64] (+)= A * W^T (transposed = false) or A * W (transposed = true), K = 64: A = hi / lo planes in tensor memory
+// (64 columns each, lane = sample), W = hi / lo K-major images of a 64 x 64 weight.  24 UMMAs 128 x 64 x 8.
+DEV void issue_linear_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t w_hi, uint32_t w_lo, bool transposed,
+                         bool accumulate) {
+    const uint32_t idesc = tc05::make_idesc_tf32_ex(kTile, kHid, false, transposed);
+    const uint32_t sbo_k = (kHid / 4) * 128;   // 2048: stride between 8-row groups of the K-major image
+#pragma unroll 1
+    for (int ks = 0; ks < kHid / 8; ++ks) {
+        uint64_t b_hi, b_lo;
+        if (!transposed) {   // K = input feature: two 16-byte chunks per step
+            b_hi = tc05::make_smem_desc_ex(w_hi + ks * 256, 128, sbo_k);
+            b_lo = tc05::make_smem_desc_ex(w_lo + ks * 256, 128, sbo_k);
+        } else {             // K = output feature = image row: one 8-row group per step; MN groups are the 16-byte K chunks
+            b_hi = tc05::make_smem_desc_ex(w_hi + ks * sbo_k, sbo_k, 128);
+            b_lo = tc05::make_smem_desc_ex(w_lo + ks * sbo_k, sbo_k, 128);
+        }
+        tc05::mma_tf32_ts(tmem_d, tmem_a_hi + 8 * ks, b_hi, idesc, accumulate || ks > 0);
+        tc05::mma_tf32_ts(tmem_d, tmem_a_lo + 8 * ks, b_hi, idesc, true);
+        tc05::mma_tf32_ts(tmem_d, tmem_a_hi + 8 * ks, b_lo, idesc, true);
+    }
+}
+// D[64 x N] = G^T * Q over the 128 samples: G [128][64] and Q [128][N] as row-written hi / lo images (lo plane = hi plane
+// address + plane bytes).  48 UMMAs 64 x N x 8; accumulator rows at TMEM lanes (m % 16) + 32 * (m / 16).
+DEV void issue_weight_grad(uint32_t tmem_d, uint32_t ga, uint32_t ga_plane_bytes, uint32_t gb, uint32_t gb_plane_bytes, int N) {
+    const uint32_t idesc = tc05::make_idesc_tf32_ex(64, N, true, true);
+#pragma unroll 1
+    for (int ks = 0; ks < kTile / 8; ++ks) {
+        const uint64_t a_hi = tc05::make_smem_desc_ex(ga + ks * 128, 128, kRowGroupStride);
+        const uint64_t a_lo = tc05::make_smem_desc_ex(ga + ga_plane_bytes + ks * 128, 128, kRowGroupStride);
+        const uint64_t b_hi = tc05::make_smem_desc_ex(gb + ks * 128, 128, kRowGroupStride);
+        const uint64_t b_lo = tc05::make_smem_desc_ex(gb + gb_plane_bytes + ks * 128, 128, kRowGroupStride);
+        tc05::mma_tf32(tmem_d, a_hi, b_hi, idesc, ks > 0);
+        tc05::mma_tf32(tmem_d, a_lo, b_hi, idesc, true);
+        tc05::mma_tf32(tmem_d, a_hi, b_lo, idesc, true);
+    }
+}
+
+}  // namespace tctrain

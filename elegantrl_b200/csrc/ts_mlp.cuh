@@ -115,6 +115,63 @@ DEV void hidden_chunk_inplace(uint32_t taddr) {
     tc05::tmem_st_32x32b_x16(taddr, w);
 }
 
+// tcgen05.wait::ld that is ALSO a data dependence on the 16 destination registers of an earlier tcgen05.ld: the loads are
+// asynchronous, and a software-pipelined sequence (issue the next chunk's load, then work on the current chunk) must keep
+// the compiler from scheduling a use of the registers above the wait.
+DEV void tmem_ld_wait_tied(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :: "memory");
+}
+// GELU -> {hi, lo} fp16 pairs of 16 pre-activations already in registers, written back to columns [taddr, taddr + 16)
+template <bool GELU>
+DEV void hidden_chunk_from_regs(uint32_t taddr, const float (&v)[16]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        float2 g = make_float2(v[2 * p], v[2 * p + 1]);
+        if (GELU) g = gelu_fast2(g);
+        const float2 hi = make_float2(tc05::tf32_hi(g.x), tc05::tf32_hi(g.y));
+        const float2 lo = __ffma2_rn(hi, splat(-1.0f), g);
+        w[2 * p] = tc05::pack_f16x2(lo.x, hi.x);
+        w[2 * p + 1] = tc05::pack_f16x2(lo.y, hi.y);
+    }
+    tc05::tmem_st_32x32b_x16(taddr, w);
+}
+// 16 terms of the head's dot product from registers
+template <bool GELU>
+DEV float2 head_chunk_from_regs(const float (&v)[16], const float* w3c, float2 out2) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 w = *reinterpret_cast<const float4*>(w3c + q4 * 4);
+        float2 g01 = make_float2(v[q4 * 4 + 0], v[q4 * 4 + 1]), g23 = make_float2(v[q4 * 4 + 2], v[q4 * 4 + 3]);
+        if (GELU) { g01 = gelu_fast2(g01); g23 = gelu_fast2(g23); }
+        out2 = __ffma2_rn(g01, make_float2(w.x, w.y), out2);
+        out2 = __ffma2_rn(g23, make_float2(w.z, w.w), out2);
+    }
+    return out2;
+}
+// head with the tensor-memory loads software-pipelined: the load of chunk c + 1 is in flight while chunk c is evaluated
+template <bool GELU>
+DEV float head_dot_pipelined(uint32_t taddr_d, const float* w3, float b3) {
+    float2 out2 = make_float2(b3, 0.0f);
+    float a[16], b[16];
+    tc05::tmem_ld_32x32b_x16(taddr_d, a);
+    tmem_ld_wait_tied(a);
+    tc05::tmem_ld_32x32b_x16(taddr_d + 16, b);
+    out2 = head_chunk_from_regs<GELU>(a, w3, out2);
+    tmem_ld_wait_tied(b);
+    tc05::tmem_ld_32x32b_x16(taddr_d + 32, a);
+    out2 = head_chunk_from_regs<GELU>(b, w3 + 16, out2);
+    tmem_ld_wait_tied(a);
+    tc05::tmem_ld_32x32b_x16(taddr_d + 48, b);
+    out2 = head_chunk_from_regs<GELU>(a, w3 + 32, out2);
+    tmem_ld_wait_tied(b);
+    out2 = head_chunk_from_regs<GELU>(b, w3 + 48, out2);
+    return out2.x + out2.y;
+}
+
 // head: sum_j GELU(Z2[j]) * w3[j] + b3 for this thread's row; w3 = 64 floats in shared memory (16-byte aligned)
 template <bool GELU>
 DEV float head_dot(uint32_t taddr_d, const float* w3, float b3) {

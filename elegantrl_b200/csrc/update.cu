@@ -11,11 +11,13 @@
 // moment tensors, and re-zeroes the buffer for the next minibatch.  Sharded (multi-GPU) callers stop after the
 // gradient phase (b200rl_ppo_grads), all-reduce the flat buffer, then run b200rl_ppo_apply.
 #include <cooperative_groups.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <string.h>
 
 #include "mlp_tile.cuh"
+#include "update_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -27,36 +29,6 @@ constexpr int kMaxGradCtas = 296;  // per net: 2 x 148 SMs; larger minibatches w
 constexpr int kMultiTileMin = 148; // from this many tiles on, the 128-register instantiation (2 CTAs per SM) is used: measured
                                    // 0.42 vs 0.51 ms per update_net at 4 x 8 192 samples, 1.64 vs 2.69 ms at 4 x 65 536
 using UT = SmemTile<UTB>;
-
-struct AdamScalars {
-    float step_size;  // lr / (1 - beta1^t)
-    float bc2_sqrt;   // sqrt(1 - beta2^t)
-};
-
-struct UpdateArgs {
-    b200rl_net net[2];  // 0 = actor, 1 = critic
-    b200rl_adam opt[2];
-    AdamScalars adam[2];
-    b200rl_train_buffer buf;
-    b200rl_ppo_hyper hp;
-    const int64_t* ids;  // [local_batch] or nullptr
-    uint64_t seed, draw;
-    int local_batch, global_batch;
-    float* grads;              // flat: actor tensors then critic tensors
-    int grad_off[2];           // float offset of each net's first tensor
-    int grad_numel[2];
-    WorkspaceHeader* hdr;
-    double* loss_sums;         // [3] obj_critic, obj_surrogate, obj_entropy (sums over updates)
-    int fused_apply;
-    int smem_scalar_off;       // float offset of the per-sample scalar block in dynamic smem
-    int maxdim;
-    int stage_weights;         // parameters of the net fit in shared memory: stage them per minibatch
-    int smem_weight_off;       // float offset of the staged parameters in dynamic smem
-    int smem_gacc_off;         // float offset of the per-CTA gradient accumulator (large minibatches), or -1
-    int update_times;          // persistent (cluster) kernel: minibatches per launch
-    int grad_stride;           // floats between the two gradient buffers of the persistent kernel
-    float* out_scalars;        // persistent kernel: means of the three logged scalars
-};
 
 // dW[j][k] += sum_b dZ[j][b] * X[k][b];  db[j] += sum_b dZ[j][b]      (RED.ADD into the flat buffer)
 // `atomic` = false: gW / gb point at this CTA's private shared-memory accumulator (every element is owned by exactly one
@@ -158,122 +130,6 @@ DEV void data_grad(const float* Wp, const float* dZ, const float* G, float* dZpr
     constexpr int NOL = kUpdThreads / (UTB / 4);
     if (K <= NOL * 2) data_grad_tile<WM, 2>(Wp, dZ, G, dZprev, J, K);
     else data_grad_tile<WM, 4>(Wp, dZ, G, dZprev, J, K);
-}
-
-DEV float block_sum(float v, float* red /*[32]*/) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.0f;
-#pragma unroll
-    for (int w = 0; w < kUpdThreads / 32; ++w) t += red[w];
-    return t;
-}
-
-// torch.optim.Adam single-tensor update, op order of torch (_single_tensor_adam), no FMA contraction
-DEV void adam_one(float& p, float& m, float& v, float g, float b1, float b2, float eps, const AdamScalars& as) {
-    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - b1));                 // exp_avg.lerp_(grad, 1 - beta1)
-    v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(1.0f - b2, g), g));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), as.bc2_sqrt), eps);
-    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-as.step_size, m), denom));         // addcdiv_(exp_avg, denom, -step_size)
-}
-
-// clip_grad_norm_ + Adam.step for one net.  The whole CTA computes the norm of the net's gradient; it then updates
-// the part `part` of `nparts` of every tensor (nparts = 1: the whole net; > 1: the CTAs of a cluster share the net).
-DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
-                   float clip_grad_norm, float* red, int part = 0, int nparts = 1) {
-    // squared norm of the whole gradient: batches of 8 independent L2 loads per thread (a plain loop would wait for
-    // one ~700-cycle load per iteration)
-    float ss = 0.0f;
-    for (int i0 = threadIdx.x; i0 < numel; i0 += 8 * kUpdThreads) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (i0 + q * kUpdThreads < numel) ? __ldcg(g + i0 + q * kUpdThreads) : 0.0f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) ss = fmaf(v[q], v[q], ss);
-    }
-    float total_norm = sqrtf(block_sum(ss, red));
-    float coef = 1.0f;
-    if (clip_grad_norm > 0.0f) coef = fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f);
-    const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps;
-    const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
-    const int first = part * kUpdThreads + threadIdx.x, stride = nparts * kUpdThreads;
-    // Every tensor is visited in rounds of up to kBatch tensors: all loads of a round are issued before any
-    // arithmetic / store, so their (L2) latencies overlap instead of adding up tensor after tensor.
-    constexpr int kBatch = 4;
-    int off = 0;
-    for (int t0 = 0; t0 < n_tensors; t0 += kBatch) {
-        float* P[kBatch]; float* M[kBatch]; float* V[kBatch];
-        int cnt[kBatch], goff[kBatch];
-        bool vecs[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            const int ti = t0 + q;
-            cnt[q] = 0; goff[q] = off; vecs[q] = false; P[q] = M[q] = V[q] = nullptr;
-            if (ti < n_tensors) {
-                const int l = ti >> 1;
-                if (ti == 2 * net.num_linear) {
-                    P[q] = net.action_std_log; M[q] = opt.exp_avg_std; V[q] = opt.exp_avg_sq_std; cnt[q] = net.dims[net.num_linear];
-                } else if ((ti & 1) == 0) {
-                    P[q] = net.weight[l]; M[q] = opt.exp_avg_w[l]; V[q] = opt.exp_avg_sq_w[l]; cnt[q] = net.dims[l + 1] * net.dims[l];
-                } else {
-                    P[q] = net.bias[l]; M[q] = opt.exp_avg_b[l]; V[q] = opt.exp_avg_sq_b[l]; cnt[q] = net.dims[l + 1];
-                }
-                vecs[q] = ((cnt[q] & 3) == 0) &&
-                          (((reinterpret_cast<uintptr_t>(g + off) | reinterpret_cast<uintptr_t>(P[q]) | reinterpret_cast<uintptr_t>(M[q]) |
-                             reinterpret_cast<uintptr_t>(V[q])) & 15) == 0);
-                off += cnt[q];
-            }
-        }
-        // first item of every tensor of the round (covers whole tensors up to 4 * stride floats): batched loads
-        float4 gg[kBatch], pp[kBatch], mm[kBatch], vv[kBatch];
-        bool have[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            have[q] = vecs[q] && first < (cnt[q] >> 2);
-            if (have[q]) {
-                gg[q] = __ldcg(reinterpret_cast<const float4*>(g + goff[q]) + first);
-                pp[q] = __ldcg(reinterpret_cast<const float4*>(P[q]) + first);
-                mm[q] = __ldcg(reinterpret_cast<const float4*>(M[q]) + first);
-                vv[q] = __ldcg(reinterpret_cast<const float4*>(V[q]) + first);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            if (have[q]) {
-                adam_one(pp[q].x, mm[q].x, vv[q].x, gg[q].x * coef, b1, b2, eps, as);
-                adam_one(pp[q].y, mm[q].y, vv[q].y, gg[q].y * coef, b1, b2, eps, as);
-                adam_one(pp[q].z, mm[q].z, vv[q].z, gg[q].z * coef, b1, b2, eps, as);
-                adam_one(pp[q].w, mm[q].w, vv[q].w, gg[q].w * coef, b1, b2, eps, as);
-                reinterpret_cast<float4*>(P[q])[first] = pp[q];
-                reinterpret_cast<float4*>(M[q])[first] = mm[q];
-                reinterpret_cast<float4*>(V[q])[first] = vv[q];
-            }
-        }
-        // remaining items (large tensors) and tensors that cannot be accessed as float4
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            if (vecs[q]) {
-                const float4* g4 = reinterpret_cast<const float4*>(g + goff[q]);
-                float4 *p4 = reinterpret_cast<float4*>(P[q]), *m4 = reinterpret_cast<float4*>(M[q]), *v4 = reinterpret_cast<float4*>(V[q]);
-                for (int i = first + stride; i < (cnt[q] >> 2); i += stride) {
-                    float4 a = __ldcg(g4 + i), b = __ldcg(p4 + i), c = __ldcg(m4 + i), d = __ldcg(v4 + i);
-                    adam_one(b.x, c.x, d.x, a.x * coef, b1, b2, eps, as);
-                    adam_one(b.y, c.y, d.y, a.y * coef, b1, b2, eps, as);
-                    adam_one(b.z, c.z, d.z, a.z * coef, b1, b2, eps, as);
-                    adam_one(b.w, c.w, d.w, a.w * coef, b1, b2, eps, as);
-                    p4[i] = b; m4[i] = c; v4[i] = d;
-                }
-            } else {
-                for (int i = first; i < cnt[q]; i += stride) {
-                    float pi = __ldcg(P[q] + i), mi = __ldcg(M[q] + i), vi = __ldcg(V[q] + i);
-                    adam_one(pi, mi, vi, __ldcg(g + goff[q] + i) * coef, b1, b2, eps, as);
-                    P[q][i] = pi; M[q][i] = mi; V[q][i] = vi;
-                }
-            }
-        }
-    }
 }
 
 // Gradient phase of one (sample tile, net): gather -> forward -> loss -> backward, RED.ADD into `grads` (flat buffer
@@ -578,7 +434,7 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_grads_kernel(const __grid_con
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+    apply_net<kUpdThreads>(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
     __syncthreads();
     for (int i = threadIdx.x; i < A.grad_numel[ni]; i += kUpdThreads) A.grads[A.grad_off[ni] + i] = 0.0f;
     if (threadIdx.x == 0) A.hdr->ticket[ni] = 0u;
@@ -614,7 +470,7 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_update_cluster_kernel(const _
         cluster.sync();
         PHASE_MARK(11);
         // this net's CTAs share its clip + Adam; they also re-zero the other gradient buffer for minibatch u + 1
-        apply_net(A.net[ni], A.opt[ni], s_adam, gcur + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red, tile, tiles);
+        apply_net<kUpdThreads>(A.net[ni], A.opt[ni], s_adam, gcur + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red, tile, tiles);
         PHASE_MARK(12);
         for (int i = blockIdx.x * kUpdThreads + threadIdx.x; i < gtotal; i += gridDim.x * kUpdThreads) gnext[i] = 0.0f;
         __threadfence();
@@ -628,7 +484,7 @@ __global__ void __launch_bounds__(kUpdThreads) ppo_update_cluster_kernel(const _
 __global__ void __launch_bounds__(kUpdThreads) ppo_apply_kernel(const __grid_constant__ UpdateArgs A) {
     __shared__ float red[32];
     const int ni = blockIdx.x;  // one CTA per net
-    apply_net(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
+    apply_net<kUpdThreads>(A.net[ni], A.opt[ni], A.adam[ni], A.grads + A.grad_off[ni], A.grad_numel[ni], A.hp.clip_grad_norm, red);
 }
 
 // One thread per sampled transition: draw / read its index, gather the six fields, normalise the advantage, and write a
@@ -768,8 +624,36 @@ int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* critic, b200rl_
     A.seed = seed;
     B200RL_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)b200rl_workspace_bytes(actor, critic), stream));
     const int tiles = (batch_size + UTB - 1) / UTB;
+    // B200RL_UPDATE: unset / "tc" -> the tcgen05 kernels (update_tc.cu) when the nets have their shape, else the generic ones;
+    // "cluster" / "multilaunch" -> the generic FP32-pipe kernels below (kept as the cross-check; the tests run all three)
     const char* mode = getenv("B200RL_UPDATE");
     const bool want_multi = mode && strcmp(mode, "multilaunch") == 0;
+    const bool want_generic = want_multi || (mode && strcmp(mode, "cluster") == 0);
+    if (!want_generic && b200rl_update_tc_eligible(actor, critic, hyper)) {
+        const int tiles128 = (batch_size + 127) / 128;
+        A.ids = ids;
+        A.draw = draw_offset;
+        if (tiles128 == 1) {   // the whole update_net loop as ONE persistent launch (two CTAs that never meet)
+            A.update_times = update_times;
+            A.out_scalars = out_scalars;
+            if (int rc = b200rl_launch_update_tc(A, 1, stream)) return rc;
+            B200RL_COUNT_LAUNCH(1);
+        } else {
+            for (int u = 0; u < update_times; ++u) {
+                A.ids = ids ? ids + (size_t)u * batch_size : nullptr;
+                A.draw = draw_offset + (uint64_t)u;
+                A.adam[0] = adam_scalars(actor_opt, actor_opt->step + u + 1);
+                A.adam[1] = adam_scalars(critic_opt, critic_opt->step + u + 1);
+                if (int rc = b200rl_launch_update_tc(A, tiles128, stream)) return rc;
+            }
+            loss_means_kernel<<<1, 32, 0, stream>>>(A.loss_sums, 1.0 / (double)update_times, out_scalars);
+            B200RL_COUNT_LAUNCH(update_times + 1);
+            B200RL_CHECK_CUDA(cudaGetLastError());
+        }
+        actor_opt->step += update_times;
+        critic_opt->step += update_times;
+        return 0;
+    }
     if (2 * tiles <= 8 && !want_multi) {
         // small minibatches (the Config default 128): the whole update_net loop as ONE persistent cluster launch
         A.update_times = update_times;
@@ -814,6 +698,53 @@ int b200rl_ppo_update(const b200rl_net* actor, const b200rl_net* critic, b200rl_
     return 0;
 }
 
+int b200rl_ppo_update_sharded(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt, b200rl_adam* critic_opt,
+                              const b200rl_train_buffer* buffer, const b200rl_ppo_hyper* hyper, int32_t batch_size,
+                              int32_t update_times, const int64_t* ids, uint64_t seed, uint64_t draw_offset,
+                              const double* stat_sums, int64_t count_all, int64_t count_lattice, float* adv_stats_out,
+                              float* out_scalars, void* workspace, int64_t workspace_bytes, const b200rl_peer_exchange* px,
+                              void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200RL_REQUIRE(actor_opt && critic_opt && out_scalars && px && stat_sums, "ppo_update_sharded: NULL argument");
+    B200RL_REQUIRE(px->world >= 1 && px->world <= B200RL_MAX_PEERS && px->rank >= 0 && px->rank < px->world,
+                   "ppo_update_sharded: rank %d of %d", px->rank, px->world);
+    B200RL_REQUIRE(batch_size >= px->world && batch_size % px->world == 0 && batch_size / px->world <= 128 && update_times >= 1,
+                   "ppo_update_sharded: batch_size=%d must be a multiple of world=%d with at most 128 samples per rank", batch_size,
+                   px->world);
+    for (int r = 0; r < px->world; ++r)
+        B200RL_REQUIRE(px->data[r] && px->flags[r], "ppo_update_sharded: peer %d is not mapped", r);
+    if (int rc = check_buffer(buffer)) return rc;
+    B200RL_REQUIRE(buffer->horizon_len >= 1, "ppo_update_sharded: needs the [H, N] shard, not packed records");
+    UpdateArgs A{};
+    size_t smem = 0;
+    if (int rc = fill_args(A, actor, critic, actor_opt, critic_opt, buffer, hyper, workspace, workspace_bytes, &smem)) return rc;
+    B200RL_REQUIRE(b200rl_update_tc_eligible(actor, critic, hyper),
+                   "ppo_update_sharded: nets must be S -> 64 -> 64 -> OUT GELU (b200rl_update_tc_supported)");
+    A.loss_sums = A.hdr->loss_sums;
+    A.fused_apply = 1;
+    A.local_batch = batch_size / px->world;
+    A.global_batch = batch_size;
+    A.seed = seed;
+    A.ids = ids;
+    A.draw = draw_offset;
+    A.update_times = update_times;
+    A.out_scalars = out_scalars;
+    A.px_on = 1;
+    A.px = *px;
+    A.stat_sums = stat_sums;
+    A.count_all = (double)count_all;
+    A.count_lat = (double)count_lattice;
+    A.stats_out = adv_stats_out;
+    B200RL_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)b200rl_workspace_bytes(actor, critic), stream));
+    if (int rc = b200rl_launch_update_tc(A, 1, stream)) return rc;
+    B200RL_COUNT_LAUNCH(1);
+    actor_opt->step += update_times;
+    critic_opt->step += update_times;
+    return 0;
+}
+
+int64_t b200rl_workspace_error_offset(void) { return (int64_t)offsetof(WorkspaceHeader, pad); }
+
 int b200rl_ppo_grads(const b200rl_net* actor, const b200rl_net* critic, const b200rl_train_buffer* buffer,
                      const b200rl_ppo_hyper* hyper, int32_t local_batch, int32_t global_batch, const int64_t* ids,
                      uint64_t seed, uint64_t draw_offset, double* loss_sums, void* workspace, int64_t workspace_bytes,
@@ -834,10 +765,19 @@ int b200rl_ppo_grads(const b200rl_net* actor, const b200rl_net* critic, const b2
     A.seed = seed;
     A.draw = draw_offset;
     const int tiles = (local_batch + UTB - 1) / UTB;
+    B200RL_CHECK_CUDA(cudaMemsetAsync(A.grads, 0, (size_t)(A.grad_off[1] + A.grad_numel[1]) * sizeof(float), stream));
+    {
+        const char* mode = getenv("B200RL_UPDATE");
+        const bool want_generic = mode && (strcmp(mode, "multilaunch") == 0 || strcmp(mode, "cluster") == 0);
+        if (!want_generic && b200rl_update_tc_eligible(actor, critic, hyper)) {
+            if (int rc = b200rl_launch_update_tc(A, (local_batch + 127) / 128, stream)) return rc;
+            B200RL_COUNT_LAUNCH(1);
+            return 0;
+        }
+    }
     const bool multi = A.smem_gacc_off >= 0 && tiles >= kMultiTileMin;
     auto kern = multi ? ppo_grads_kernel<true> : ppo_grads_kernel<false>;
     B200RL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200RL_CHECK_CUDA(cudaMemsetAsync(A.grads, 0, (size_t)(A.grad_off[1] + A.grad_numel[1]) * sizeof(float), stream));
     kern<<<dim3((unsigned)(multi ? std::min(tiles, kMaxGradCtas) : tiles), 2), kUpdThreads, smem, stream>>>(A);
     B200RL_COUNT_LAUNCH(1);
     B200RL_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,164 @@
+// Pieces shared by the two PPO-update implementations (update.cu: generic depth / width on the FP32 pipe; update_tc.cu:
+// S -> 64 -> 64 -> OUT GELU nets on tcgen05): the kernel argument block, torch.optim.Adam's arithmetic and the per-net
+// clip_grad_norm_ + Adam.step (reference elegantrl/agents/AgentBase.py:239-248).
+#pragma once
+#include "common.cuh"
+
+struct AdamScalars {
+    float step_size;  // lr / (1 - beta1^t)
+    float bc2_sqrt;   // sqrt(1 - beta2^t)
+};
+
+struct UpdateArgs {
+    b200rl_net net[2];  // 0 = actor, 1 = critic
+    b200rl_adam opt[2];
+    AdamScalars adam[2];
+    b200rl_train_buffer buf;
+    b200rl_ppo_hyper hp;
+    const int64_t* ids;  // [local_batch] or nullptr
+    uint64_t seed, draw;
+    int local_batch, global_batch;
+    float* grads;              // flat: actor tensors then critic tensors
+    int grad_off[2];           // float offset of each net's first tensor
+    int grad_numel[2];
+    WorkspaceHeader* hdr;
+    double* loss_sums;         // [3] obj_critic, obj_surrogate, obj_entropy (sums over updates)
+    int fused_apply;
+    int smem_scalar_off;       // float offset of the per-sample scalar block in dynamic smem
+    int maxdim;
+    int stage_weights;         // parameters of the net fit in shared memory: stage them per minibatch
+    int smem_weight_off;       // float offset of the staged parameters in dynamic smem
+    int smem_gacc_off;         // float offset of the per-CTA gradient accumulator (large minibatches), or -1
+    int update_times;          // persistent (cluster) kernel: minibatches per launch
+    int grad_stride;           // floats between the two gradient buffers of the persistent kernel
+    float* out_scalars;        // persistent kernel: means of the three logged scalars
+    // env-sharded update with the in-kernel gradient exchange over peer memory (update_tc.cu, b200rl_ppo_update_sharded)
+    int px_on;
+    b200rl_peer_exchange px;
+    const double* stat_sums;   // this shard's advantage sums (b200rl_gae)
+    double count_all, count_lat;
+    float* stats_out;          // [4] reduced statistics
+};
+
+// update_tc.cu: the tcgen05 implementation for S -> 64 -> 64 -> OUT GELU nets
+bool b200rl_update_tc_eligible(const b200rl_net* actor, const b200rl_net* critic, const b200rl_ppo_hyper* hp);
+int b200rl_launch_update_tc(const UpdateArgs& A, int tiles, cudaStream_t stream);
+
+template <int NT>
+DEV float block_sum(float v, float* red /*[32]*/) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += red[w];
+    return t;
+}
+
+// torch.optim.Adam single-tensor update, op order of torch (_single_tensor_adam), no FMA contraction
+DEV void adam_one(float& p, float& m, float& v, float g, float b1, float b2, float eps, const AdamScalars& as) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - b1));                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(1.0f - b2, g), g));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), as.bc2_sqrt), eps);
+    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-as.step_size, m), denom));         // addcdiv_(exp_avg, denom, -step_size)
+}
+
+// clip_grad_norm_ + Adam.step for one net.  The whole CTA computes the norm of the net's gradient; it then updates
+// the part `part` of `nparts` of every tensor (nparts = 1: the whole net; > 1: the CTAs of a cluster share the net).
+template <int NT>
+DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
+                   float clip_grad_norm, float* red, int part = 0, int nparts = 1) {
+    // squared norm of the whole gradient: batches of 8 independent L2 loads per thread (a plain loop would wait for
+    // one ~700-cycle load per iteration)
+    float ss = 0.0f;
+    for (int i0 = threadIdx.x; i0 < numel; i0 += 8 * NT) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (i0 + q * NT < numel) ? __ldcg(g + i0 + q * NT) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ss = fmaf(v[q], v[q], ss);
+    }
+    float total_norm = sqrtf(block_sum<NT>(ss, red));
+    float coef = 1.0f;
+    if (clip_grad_norm > 0.0f) coef = fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f);
+    const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps;
+    const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
+    const int first = part * NT + threadIdx.x, stride = nparts * NT;
+    // Every tensor is visited in rounds of up to kBatch tensors: all loads of a round are issued before any
+    // arithmetic / store, so their (L2) latencies overlap instead of adding up tensor after tensor.
+    constexpr int kBatch = 4;
+    int off = 0;
+    for (int t0 = 0; t0 < n_tensors; t0 += kBatch) {
+        float* P[kBatch]; float* M[kBatch]; float* V[kBatch];
+        int cnt[kBatch], goff[kBatch];
+        bool vecs[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const int ti = t0 + q;
+            cnt[q] = 0; goff[q] = off; vecs[q] = false; P[q] = M[q] = V[q] = nullptr;
+            if (ti < n_tensors) {
+                const int l = ti >> 1;
+                if (ti == 2 * net.num_linear) {
+                    P[q] = net.action_std_log; M[q] = opt.exp_avg_std; V[q] = opt.exp_avg_sq_std; cnt[q] = net.dims[net.num_linear];
+                } else if ((ti & 1) == 0) {
+                    P[q] = net.weight[l]; M[q] = opt.exp_avg_w[l]; V[q] = opt.exp_avg_sq_w[l]; cnt[q] = net.dims[l + 1] * net.dims[l];
+                } else {
+                    P[q] = net.bias[l]; M[q] = opt.exp_avg_b[l]; V[q] = opt.exp_avg_sq_b[l]; cnt[q] = net.dims[l + 1];
+                }
+                vecs[q] = ((cnt[q] & 3) == 0) &&
+                          (((reinterpret_cast<uintptr_t>(g + off) | reinterpret_cast<uintptr_t>(P[q]) | reinterpret_cast<uintptr_t>(M[q]) |
+                             reinterpret_cast<uintptr_t>(V[q])) & 15) == 0);
+                off += cnt[q];
+            }
+        }
+        // first item of every tensor of the round (covers whole tensors up to 4 * stride floats): batched loads
+        float4 gg[kBatch], pp[kBatch], mm[kBatch], vv[kBatch];
+        bool have[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            have[q] = vecs[q] && first < (cnt[q] >> 2);
+            if (have[q]) {
+                gg[q] = __ldcg(reinterpret_cast<const float4*>(g + goff[q]) + first);
+                pp[q] = __ldcg(reinterpret_cast<const float4*>(P[q]) + first);
+                mm[q] = __ldcg(reinterpret_cast<const float4*>(M[q]) + first);
+                vv[q] = __ldcg(reinterpret_cast<const float4*>(V[q]) + first);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            if (have[q]) {
+                adam_one(pp[q].x, mm[q].x, vv[q].x, gg[q].x * coef, b1, b2, eps, as);
+                adam_one(pp[q].y, mm[q].y, vv[q].y, gg[q].y * coef, b1, b2, eps, as);
+                adam_one(pp[q].z, mm[q].z, vv[q].z, gg[q].z * coef, b1, b2, eps, as);
+                adam_one(pp[q].w, mm[q].w, vv[q].w, gg[q].w * coef, b1, b2, eps, as);
+                reinterpret_cast<float4*>(P[q])[first] = pp[q];
+                reinterpret_cast<float4*>(M[q])[first] = mm[q];
+                reinterpret_cast<float4*>(V[q])[first] = vv[q];
+            }
+        }
+        // remaining items (large tensors) and tensors that cannot be accessed as float4
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            if (vecs[q]) {
+                const float4* g4 = reinterpret_cast<const float4*>(g + goff[q]);
+                float4 *p4 = reinterpret_cast<float4*>(P[q]), *m4 = reinterpret_cast<float4*>(M[q]), *v4 = reinterpret_cast<float4*>(V[q]);
+                for (int i = first + stride; i < (cnt[q] >> 2); i += stride) {
+                    float4 a = __ldcg(g4 + i), b = __ldcg(p4 + i), c = __ldcg(m4 + i), d = __ldcg(v4 + i);
+                    adam_one(b.x, c.x, d.x, a.x * coef, b1, b2, eps, as);
+                    adam_one(b.y, c.y, d.y, a.y * coef, b1, b2, eps, as);
+                    adam_one(b.z, c.z, d.z, a.z * coef, b1, b2, eps, as);
+                    adam_one(b.w, c.w, d.w, a.w * coef, b1, b2, eps, as);
+                    p4[i] = b; m4[i] = c; v4[i] = d;
+                }
+            } else {
+                for (int i = first; i < cnt[q]; i += stride) {
+                    float pi = __ldcg(P[q] + i), mi = __ldcg(M[q] + i), vi = __ldcg(V[q] + i);
+                    adam_one(pi, mi, vi, __ldcg(g + goff[q] + i) * coef, b1, b2, eps, as);
+                    P[q][i] = pi; M[q][i] = mi; V[q][i] = vi;
+                }
+            }
+        }
+    }
+}
+

@@ -1,0 +1,664 @@
+// PPO minibatch update on tcgen05 for the reference's default net shape: S -> 64 -> 64 -> OUT GELU actor and critic
+// (S <= 11, OUT <= 8; BASELINE configs[1]: 3 -> 64 -> 64 -> 1).  Same contract, arguments and results as update.cu
+// (reference AgentPPO.update_objectives, elegantrl/agents/AgentPPO.py:173-205; AgentBase.optimizer_backward,
+// elegantrl/agents/AgentBase.py:239-248); every other shape keeps the generic FP32-pipe kernels of update.cu.
+//
+// One CTA = one tile of 128 sampled transitions of ONE net (grid = tiles x 2), thread = sample = TMEM lane.  Every dense
+// contraction of the forward AND backward pass is a tcgen05 tile (3xTF32: hi / lo planes, fp32 accumulate in TMEM):
+//   L1   Z1 [128 x 64] = x~ B1^T            x~ = [x_hi, 1, x_lo, 0] (bias folded), K = round_up(2 S + 1, 8)      SS
+//   L2   Z2 [128 x 64] = b2 + H1 W2^T       H1 = GELU(Z1) as hi / lo planes in tensor memory                     TS
+//   dH1  [128 x 64]    = dZ2 W2             dZ2 planes in tensor memory; W2's forward image read MN-major        TS
+//   G2   [ 64 x 72]    = dZ2^T [H1 | 1]     = [dW2 | db2]: contraction over the SAMPLES; both operands are
+//   G1   [ 64 x N1]    = dZ1^T [X  | 1]     = [dW1 | db1]  row-written shared-memory images read MN-major         SS
+// GELU / GELU', the head (64 -> OUT), the PPO loss and its derivative run on CUDA cores, thread = sample; the head's
+// weight gradient is reduced with shuffles.  Gradients go to the flat buffer of the workspace; clip + Adam is the shared
+// apply_net (update_common.cuh).  With one tile per net (batch_size <= 128: the Config default) the kernel is PERSISTENT:
+// all minibatches of update_net in one launch, two CTAs that never synchronise with each other.
+#include <stdlib.h>
+#include <string.h>
+
+#include "tc_train.cuh"
+#include "update_common.cuh"
+
+namespace {
+
+using namespace tctrain;
+
+constexpr int kT = 128;
+constexpr int kMaxS = 11, kMaxOut = 8, kK1Max = 24;
+
+// ---- dynamic shared memory map (bytes)
+constexpr int kOffW2 = 0;                                      // W2 hi / lo K-major images
+constexpr int kOffGA = kOffW2 + 2 * kWPlaneBytes;              // dZ rows (hi / lo): A operand of G2, then of G1
+constexpr int kOffGB2 = kOffGA + 2 * kGAPlaneBytes;            // [H1 | 1 | 0] rows (hi / lo)
+constexpr int kGB1PlaneBytes = 16 * kT * 4;
+constexpr int kOffGB1 = kOffGB2 + 2 * kGB2PlaneBytes;          // [X | 1 | 0] rows (hi / lo)
+constexpr int kA1Bytes = kT * kK1Max * 4;
+constexpr int kOffA1 = kOffGB1 + 2 * kGB1PlaneBytes;           // x~ rows, K-major
+constexpr int kB1PlaneBytes = kHid * kK1Max * 4;
+constexpr int kOffB1 = kOffA1 + kA1Bytes;                      // layer-1 B planes
+constexpr int kOffBB = kOffB1 + 2 * kB1PlaneBytes;             // [b2_hi, b2_lo, 0...] rows, K = 8
+constexpr int kOffAC = kOffBB + kHid * 8 * 4;                  // constant A = [1, 1, 0...], K = 8
+constexpr int kOffSmall = kOffAC + kT * 8 * 4;
+constexpr int kSmW3 = 0, kSmB3 = 512, kSmStd = 520, kSmAvg = 528, kSmSd = 544, kSmGW3 = 560, kSmGB3 = 1072, kSmGStd = 1080,
+              kSmallFloats = 1088;
+constexpr int kOffBar = kOffSmall + kSmallFloats * 4;
+constexpr int kSmemBytes = kOffBar + 16;
+static_assert(kSmemBytes <= 226 * 1024, "shared memory budget");
+
+// ---- tensor memory columns
+constexpr uint32_t cZ1 = 0, cPhi = 64, cPlo = 128, cZ2 = 192, cG2 = 256, cG1 = 328;
+
+// ---- peer-memory exchange (env-sharded update): system-scope release / acquire flags, relaxed system-scope data loads
+DEV void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+DEV uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV float4 ld_relaxed_sys_v4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+DEV uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int kPxStatFloats = 8;   // 4 doubles at the head of every exchange buffer
+DEV int px_segment(int numel) { return (numel + 4 + 3) & ~3; }   // gradient + 3 loss partial sums + padding
+// One exchange round of channel `chan` (0 = statistics, 1 = actor gradient, 2 = critic gradient): everything this CTA stored
+// into its own buffer becomes visible to the peers, and theirs to this CTA.  Flags only ever grow (epochs), so there is no
+// reset and no ABA; a peer that does not answer within ~2 s raises the error word of the workspace header instead of
+// hanging the GPU.
+DEV void px_round(const b200rl_peer_exchange& px, int chan, uint32_t value, WorkspaceHeader* hdr) {
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < px.world) st_release_sys(px.flags[threadIdx.x] + chan * B200RL_MAX_PEERS + px.rank, value);
+    if ((int)threadIdx.x < px.world) {
+        const uint32_t* f = px.flags[px.rank] + chan * B200RL_MAX_PEERS + threadIdx.x;
+        const uint64_t t0 = global_timer_ns();
+        while ((int32_t)(ld_acquire_sys(f) - value) < 0) {
+            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(&hdr->pad[0], 1u); break; }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_constant__ UpdateArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ float red[32];
+    __shared__ AdamScalars s_adam;
+    __shared__ int s_last;
+    __shared__ uint32_t tmem_slot;
+    float* small = reinterpret_cast<float*>(smem + kOffSmall);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ni = blockIdx.y, tile = blockIdx.x;
+    const b200rl_net& net = A.net[ni];
+    const int S = net.dims[0], OUT = net.dims[3];
+    const int K1 = (2 * S + 1 + 7) & ~7, N1 = (S + 1 + 7) & ~7;
+    const bool persistent = A.update_times > 0;
+    const int U = persistent ? A.update_times : 1;
+    const bool discrete = A.buf.discrete_actions != 0;
+    const bool gaussian = ni == 0 && !discrete;
+    const int H = A.buf.horizon_len, N = A.buf.num_envs;
+    const bool packed = (H == 0);
+    const int rec_act = A.net[0].dims[0], rec_tail = (A.net[0].dims[0] + A.net[0].dims[3] + 3) & ~3, rec = rec_tail + 4;
+    const int flags = A.hp.flags;
+    const float inv_bsz = 1.0f / (float)A.global_batch;
+
+    // ---- one-time setup
+    if (warp == 0) tc05::tmem_alloc<512>(&tmem_slot);
+    if (tid == 32) { tc05::mbar_init(bar, 1); tc05::mbar_fence_init(); }
+    for (int i = tid; i < kT * 8; i += kT)   // constant A of the bias UMMA
+        *reinterpret_cast<float*>(smem + kOffAC + tc05::operand_offset(i >> 3, i & 7, 8)) = (i & 7) < 2 ? 1.0f : 0.0f;
+    for (int i = tid; i < kA1Bytes / 4; i += kT) reinterpret_cast<float*>(smem + kOffA1)[i] = 0.0f;
+    {   // columns 64..71 of [H1 | 1 | 0]: the ones column gives db2
+        const float one[8] = {1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_hi_lo_rows8(smem + kOffGB2, smem + kOffGB2 + kGB2PlaneBytes, tid, 64, one);
+    }
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    tc05::fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
+    const uint32_t w2_hi = tc05::smem_u32(smem + kOffW2), w2_lo = w2_hi + kWPlaneBytes;
+    uint32_t phase = 0;
+    double acc_c = 0.0, acc_s = 0.0, acc_e = 0.0;   // thread 0: loss sums over the minibatches (persistent mode)
+
+    // advantage normalisation (reference :149): from the caller's statistics, or -- env-sharded -- reduced here over the shards
+    __shared__ float s_stats[2];
+    const bool sharded = A.px_on != 0;
+    bool normalise = A.buf.adv_stats != nullptr;
+    if (sharded && ni == 0) {
+        if (tid < 4) reinterpret_cast<double*>(A.px.data[A.px.rank])[tid] = A.stat_sums[tid];
+        px_round(A.px, 0, A.px.epoch + 1, A.hdr);
+        if (tid == 0) {
+            double sums[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int r = 0; r < A.px.world; ++r)
+                for (int k = 0; k < 4; ++k) {
+                    const float lo = ld_relaxed_sys(A.px.data[r] + 2 * k), hi = ld_relaxed_sys(A.px.data[r] + 2 * k + 1);
+                    sums[k] += __hiloint2double(__float_as_int(hi), __float_as_int(lo));
+                }
+            // b200rl_adv_stats' arithmetic (gae.cu)
+            const double mean = sums[0] / A.count_all;
+            const bool full = A.count_lat == 0.0;
+            const double cnt = full ? A.count_all : A.count_lat;
+            const double m = (full ? sums[0] : sums[1]) / cnt, sq = full ? sums[3] : sums[2];
+            const double var = (sq - cnt * m * m) / (cnt - 1.0);
+            float sd = (float)sqrt(var > 0.0 ? var : 0.0);
+            if (cnt < 2.0) sd = nanf("");
+            s_stats[0] = (float)mean; s_stats[1] = sd;
+            if (A.stats_out) { A.stats_out[0] = (float)mean; A.stats_out[1] = sd; A.stats_out[2] = 1.0f / (sd + 1e-5f); A.stats_out[3] = 0.0f; }
+        }
+        normalise = true;
+        __syncthreads();
+    } else if (normalise) {
+        if (tid < 2) s_stats[tid] = A.buf.adv_stats[tid];
+        __syncthreads();
+    }
+
+    // flat gradient layout of this net: W0 [64 x S], b0, W1 [64 x 64], b1, W2 [OUT x 64], b2, (action_std_log)
+    const int oB0 = kHid * S, oW1 = oB0 + kHid, oB1 = oW1 + kHid * kHid, oW2 = oB1 + kHid, oB2 = oW2 + OUT * kHid, oStd = oB2 + OUT;
+    float* const g_local = A.grads + A.grad_off[ni];
+    const int numel = A.grad_numel[ni];
+    const int px_off0 = kPxStatFloats + (ni ? px_segment(A.grad_numel[0]) : 0);
+    const int px_parity_stride = px_segment(A.grad_numel[0]) + px_segment(A.grad_numel[1]);
+
+    for (int u = 0; u < U; ++u) {
+        // env-sharded: this minibatch's gradient goes to the own exchange buffer (two alternate so that a rank that is one
+        // minibatch ahead never overwrites what a peer still reads); the reduced gradient lands in the workspace as usual
+        const int px_off = px_off0 + (u & 1) * px_parity_stride;
+        float* const g = sharded ? A.px.data[A.px.rank] + px_off : g_local;
+        // ------------------------------------------------------------ parameters -> operand images (Adam rewrote them)
+        stage_w_planes(net.weight[1], smem + kOffW2, smem + kOffW2 + kWPlaneBytes, tid, kT);
+        for (int i = tid; i < kHid * K1; i += kT) {
+            const int n = i / K1, k = i - n * K1;
+            float full = 0.0f;
+            if (k < S) full = __ldcg(net.weight[0] + n * S + k);
+            else if (k == S) full = __ldcg(net.bias[0] + n);
+            else if (k <= 2 * S) full = __ldcg(net.weight[0] + n * S + (k - S - 1));
+            const float hi = tc05::tf32_hi(full);
+            const uint32_t off = tc05::operand_offset(n, k, K1);
+            *reinterpret_cast<float*>(smem + kOffB1 + off) = hi;                                   // [W_hi, b_hi, W_hi, 0]
+            *reinterpret_cast<float*>(smem + kOffB1 + kB1PlaneBytes + off) = k <= S ? full - hi : 0.0f;   // [W_lo, b_lo, 0, 0]
+        }
+        for (int i = tid; i < kHid * 8; i += kT) {
+            const int n = i >> 3, k = i & 7;
+            const float b2 = __ldcg(net.bias[1] + n), b2hi = tc05::tf32_hi(b2);
+            *reinterpret_cast<float*>(smem + kOffBB + tc05::operand_offset(n, k, 8)) = k == 0 ? b2hi : (k == 1 ? b2 - b2hi : 0.0f);
+        }
+        for (int i = tid; i < OUT * kHid; i += kT) { small[kSmW3 + i] = __ldcg(net.weight[2] + i); small[kSmGW3 + i] = 0.0f; }
+        if (tid < OUT) {
+            small[kSmB3 + tid] = __ldcg(net.bias[2] + tid);
+            small[kSmStd + tid] = gaussian ? __ldcg(net.action_std_log + tid) : 0.0f;
+            small[kSmGB3 + tid] = 0.0f;
+            small[kSmGStd + tid] = 0.0f;
+        }
+        if (tid < S) {
+            small[kSmAvg + tid] = net.state_avg ? net.state_avg[tid] : 0.0f;
+            small[kSmSd + tid] = net.state_std ? net.state_std[tid] + 1e-4f : 1.0f;
+        }
+
+        // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n)
+        const int64_t* ids_u = A.ids ? A.ids + (persistent ? (size_t)u * A.local_batch : 0) : nullptr;
+        const uint64_t draw = A.draw + (uint64_t)u;
+        const int slot = tile * kT + tid;
+        const bool valid = slot < A.local_batch;
+        float um = 0.f, lp_old = 0.f, adv = 0.f, rs = 0.f;
+        float act[kMaxOut];
+        float x[kMaxS];
+#pragma unroll
+        for (int a = 0; a < kMaxOut; ++a) act[a] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxS; ++k) x[k] = 0.0f;
+        if (valid) {
+            const int Adim = discrete ? 1 : A.net[0].dims[3];
+            if (packed) {
+                const int64_t r = ids_u ? ids_u[slot] : (int64_t)draw * A.local_batch + slot;
+                const float* recp = A.buf.states + r * rec;
+                const float4 tail = *reinterpret_cast<const float4*>(recp + rec_tail);
+                um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
+#pragma unroll
+                for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = recp[k];
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) if (a < Adim) act[a] = recp[rec_act + a];
+            } else {
+                const int64_t id = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+                const int64_t tn = (id % H) * N + id / H;
+                um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
+                lp_old = A.buf.logprobs[tn];
+                adv = A.buf.advantages[tn];
+                if (normalise) adv = (adv - s_stats[0]) / (s_stats[1] + 1e-5f);
+                rs = A.buf.reward_sums[tn];
+#pragma unroll
+                for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = A.buf.states[tn * S + k];
+                if (discrete) act[0] = (float)reinterpret_cast<const int32_t*>(A.buf.actions)[tn];
+                else {
+#pragma unroll
+                    for (int a = 0; a < kMaxOut; ++a) if (a < Adim) act[a] = A.buf.actions[tn * Adim + a];
+                }
+            }
+        }
+        __syncthreads();   // staged small parameters (state_norm statistics) are visible
+        if (valid && net.state_avg) {
+#pragma unroll
+            for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = (x[k] - small[kSmAvg + k]) / small[kSmSd + k];
+        }
+        {   // x~ row (K-major A operand of layer 1) and the [X | 1 | 0] row (B operand of G1)
+            float xr[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xr[k] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kMaxS; ++k) {
+                if (k < S) {
+                    const float hi = tc05::tf32_hi(x[k]);
+                    *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, k, K1)) = hi;
+                    *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S + 1 + k, K1)) = x[k] - hi;
+                    xr[k] = x[k];
+                }
+            }
+            *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S, K1)) = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (k == S) xr[k] = valid ? 1.0f : 0.0f;
+            if (N1 == 8) {
+                float x8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x8[k] = xr[k];
+                store_hi_lo_rows8(smem + kOffGB1, smem + kOffGB1 + kGB1PlaneBytes, tid, 0, x8);
+            } else {
+                store_hi_lo_rows(smem + kOffGB1, smem + kOffGB1 + kGB1PlaneBytes, tid, 0, xr);
+            }
+        }
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_thread_sync();
+        __syncthreads();
+
+        // ------------------------------------------------------------ layer 1 on the tensor core
+        if (tid == 0) {
+            tc05::fence_after_thread_sync();
+            const uint32_t idesc = tc05::make_idesc_tf32(kT, kHid);
+            const uint32_t sbo = (uint32_t)(K1 / 4) * 128;
+            const uint32_t a1 = tc05::smem_u32(smem + kOffA1), b1 = tc05::smem_u32(smem + kOffB1);
+            for (int p = 0; p < 2; ++p)
+                for (int ks = 0; ks < K1 / 8; ++ks)
+                    tc05::mma_tf32(tmem_base + cZ1, tc05::make_smem_desc_ex(a1 + ks * 256, 128, sbo),
+                                   tc05::make_smem_desc_ex(b1 + p * kB1PlaneBytes + ks * 256, 128, sbo), idesc, p > 0 || ks > 0);
+            tc05::mma_commit(bar);
+        }
+        tc05::mbar_wait(bar, phase & 1); ++phase;
+        tc05::fence_after_thread_sync();
+
+        // ------------------------------------------------------------ H1 = GELU(Z1): TMEM planes (layer-2 A) + rows (G2's B)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float z[16];
+            tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
+            tc05::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+            store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, z);
+            store_hi_lo_rows(smem + kOffGB2, smem + kOffGB2 + kGB2PlaneBytes, tid, 16 * c, z);
+        }
+        tc05::tmem_st_wait();
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc05::fence_after_thread_sync();
+            tc05::mma_tf32(tmem_base + cZ2, tc05::make_smem_desc_ex(tc05::smem_u32(smem + kOffAC), 128, 256),
+                           tc05::make_smem_desc_ex(tc05::smem_u32(smem + kOffBB), 128, 256), tc05::make_idesc_tf32(kT, kHid), false);
+            issue_linear_ts(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, w2_hi, w2_lo, false, true);
+            tc05::mma_commit(bar);
+        }
+        tc05::mbar_wait(bar, phase & 1); ++phase;
+        tc05::fence_after_thread_sync();
+
+        // ------------------------------------------------------------ head (64 -> OUT) on CUDA cores
+        float out[kMaxOut];
+#pragma unroll
+        for (int a = 0; a < kMaxOut; ++a) out[a] = a < OUT ? small[kSmB3 + a] : 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float z[16];
+            tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
+            tc05::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+#pragma unroll
+            for (int a = 0; a < kMaxOut; ++a) {
+                if (a < OUT) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) out[a] = fmaf(z[j], small[kSmW3 + a * kHid + 16 * c + j], out[a]);
+                }
+            }
+        }
+
+        // ------------------------------------------------------------ loss and d loss / d output (update.cu grads_phase, same
+        // arithmetic; reference :189-204, helloworld_PPO_single_file.py:332-340 behind the variant flags)
+        float dout[kMaxOut];
+#pragma unroll
+        for (int a = 0; a < kMaxOut; ++a) dout[a] = 0.0f;
+        float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;
+        if (ni == 1) {
+            const float err = out[0] - rs;
+            float l, dl;
+            if (flags & B200RL_PPO_SMOOTH_L1) {
+                const float ae = fabsf(err);
+                l = ae < 1.0f ? 0.5f * err * err : ae - 0.5f;
+                dl = ae < 1.0f ? err : copysignf(1.0f, err);
+            } else {
+                l = err * err;
+                dl = 2.0f * err;
+            }
+            loss_c = valid ? l * um : 0.0f;
+            dout[0] = valid ? dl * um * inv_bsz : 0.0f;
+        } else {
+            float logp = 0.0f, ent = 0.0f, lse = 0.0f;
+            const int act_idx = discrete ? min(max((int)act[0], 0), OUT - 1) : 0;
+            if (discrete) {
+                float m = -INFINITY, sum = 0.0f;
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) if (a < OUT) m = fmaxf(m, out[a]);
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) if (a < OUT) sum += expf(out[a] - m);
+                lse = m + logf(sum);
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) {
+                    if (a < OUT) {
+                        const float lp = out[a] - lse;
+                        ent -= expf(lp) * lp;
+                        if (a == act_idx) logp = lp;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) {
+                    if (a < OUT) {
+                        const float sd = expf(small[kSmStd + a]);
+                        const float diff = act[a] - out[a];
+                        const float lsd = logf(sd);
+                        logp += -(diff * diff) / (2.0f * (sd * sd)) - lsd - kLogSqrt2Pi;
+                        ent += 0.5f + kLogSqrt2Pi + lsd;
+                    }
+                }
+            }
+            const float ratio = expf(logp - lp_old);
+            const float um_a = (flags & B200RL_PPO_ACTOR_UNMASKED) ? 1.0f : um;
+            float surr, dsurr_dratio;
+            if (flags & B200RL_PPO_MIN_CLIP) {
+                const float rc = fminf(fmaxf(ratio, 1.0f - A.hp.ratio_clip), 1.0f + A.hp.ratio_clip);
+                const float s1 = adv * ratio, s2 = adv * rc;
+                const bool take1 = s1 <= s2;
+                surr = take1 ? s1 : s2;
+                dsurr_dratio = take1 ? adv : ((rc == ratio) ? adv : 0.0f);
+            } else {
+                const float kappa = adv > 0.0f ? 1.0f - A.hp.ratio_clip : 1.0f + A.hp.ratio_clip;
+                surr = adv * ratio * kappa;
+                dsurr_dratio = adv * kappa;
+            }
+            float dlogp_scale = ratio;
+            if (flags & B200RL_PPO_A2C) {
+                surr = adv * logp / (float)OUT;
+                dsurr_dratio = adv / (float)OUT;
+                dlogp_scale = 1.0f;
+            }
+            loss_s = valid ? surr * um_a : 0.0f;
+            loss_e = valid ? ent * um_a : 0.0f;
+            const float ent_sign = (flags & B200RL_PPO_ENTROPY_BONUS) ? -1.0f : 1.0f;
+            const float gl = valid ? -(dsurr_dratio * dlogp_scale * um_a) * inv_bsz : 0.0f;
+            const float ge = valid ? ent_sign * A.hp.lambda_entropy * um_a * inv_bsz : 0.0f;
+            if (discrete) {
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) {
+                    if (a < OUT) {
+                        const float lp = out[a] - lse, pa = expf(lp);
+                        dout[a] = gl * ((a == act_idx ? 1.0f : 0.0f) - pa) - ge * pa * (lp + ent);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) {
+                    if (a < OUT) {   // OUT is uniform over the CTA: the warp-wide reduction below is convergent
+                        const float sd = expf(small[kSmStd + a]);
+                        const float var = sd * sd;
+                        const float diff = act[a] - out[a];
+                        dout[a] = gl * diff / var;
+                        const float dstd = warp_sum(gl * (diff * diff / var - 1.0f) + ge);
+                        if (lane == 0) atomicAdd(&small[kSmGStd + a], dstd);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < kMaxOut; ++a) {
+            if (a < OUT) {
+                const float s = warp_sum(dout[a]);
+                if (lane == 0) atomicAdd(&small[kSmGB3 + a], s);
+            }
+        }
+
+        // ------------------------------------------------------------ dZ2 = (dOut W3) * GELU'(Z2): TMEM planes + rows; dW3 by shuffles
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float z[16], gz[16], dz[16];
+            tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
+            tc05::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float dg;
+                gelu_and_grad(z[j], gz[j], dg);
+                float dh = 0.0f;
+#pragma unroll
+                for (int a = 0; a < kMaxOut; ++a) if (a < OUT) dh = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j], dh);
+                dz[j] = dh * dg;
+            }
+            store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, dz);
+            store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dz);
+#pragma unroll
+            for (int a = 0; a < kMaxOut; ++a) {
+                if (a < OUT) {
+                    float w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = dout[a] * gz[j];
+                    const float tot = warp_reduce16(w, lane);
+                    if (!(lane & 1)) atomicAdd(&small[kSmGW3 + a * kHid + 16 * c + ((lane >> 1) & 15)], tot);
+                }
+            }
+        }
+        tc05::tmem_st_wait();
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc05::fence_after_thread_sync();
+            issue_linear_ts(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, w2_hi, w2_lo, true, false);   // dH1 over Z2
+            issue_weight_grad(tmem_base + cG2, tc05::smem_u32(smem + kOffGA), kGAPlaneBytes, tc05::smem_u32(smem + kOffGB2),
+                              kGB2PlaneBytes, 72);
+            tc05::mma_commit(bar);
+        }
+        tc05::mbar_wait(bar, phase & 1); ++phase;
+        tc05::fence_after_thread_sync();
+
+        // ------------------------------------------------------------ dZ1 = dH1 * GELU'(Z1) -> rows (A operand of G1)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float dh[16], z[16];
+            tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, dh);
+            tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
+            tc05::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float gj, dg;
+                gelu_and_grad(z[j], gj, dg);
+                dh[j] *= dg;
+            }
+            store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dh);
+        }
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc05::fence_after_thread_sync();
+            issue_weight_grad(tmem_base + cG1, tc05::smem_u32(smem + kOffGA), kGAPlaneBytes, tc05::smem_u32(smem + kOffGB1),
+                              kGB1PlaneBytes, N1);
+            tc05::mma_commit(bar);
+        }
+        tc05::mbar_wait(bar, phase & 1); ++phase;
+        tc05::fence_after_thread_sync();
+
+        // ------------------------------------------------------------ gradients -> flat buffer (rows j = 16 warp + lane, lane < 16)
+        const bool atomic = !persistent;   // several CTAs (tiles / the sharded path) add into a zeroed buffer
+        {
+            const int j = 16 * warp + (lane & 15);
+            const bool row_owner = lane < 16;
+#pragma unroll 1
+            for (int c = 0; c < 9; ++c) {
+                float v[8];
+                tc05::tmem_ld_32x32b_x8(tl + cG2 + 8 * c, v);
+                tc05::tmem_ld_wait();
+                if (row_owner) {
+                    if (c < 8) {
+                        float* dst = g + oW1 + j * kHid + 8 * c;
+                        if (atomic) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dst[i] = v[i];
+                        }
+                    } else {
+                        if (atomic) atomicAdd(g + oB1 + j, v[0]); else g[oB1 + j] = v[0];
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < N1 / 8; ++c) {
+                float v[8];
+                tc05::tmem_ld_32x32b_x8(tl + cG1 + 8 * c, v);
+                tc05::tmem_ld_wait();
+                if (row_owner) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = 8 * c + i;
+                        if (k < S) { if (atomic) atomicAdd(g + j * S + k, v[i]); else g[j * S + k] = v[i]; }
+                        else if (k == S) { if (atomic) atomicAdd(g + oB0 + j, v[i]); else g[oB0 + j] = v[i]; }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // the shared-memory accumulators of the head are complete
+        for (int i = tid; i < OUT * kHid; i += kT) { if (atomic) atomicAdd(g + oW2 + i, small[kSmGW3 + i]); else g[oW2 + i] = small[kSmGW3 + i]; }
+        if (tid < OUT) {
+            if (atomic) atomicAdd(g + oB2 + tid, small[kSmGB3 + tid]); else g[oB2 + tid] = small[kSmGB3 + tid];
+            if (gaussian) { if (atomic) atomicAdd(g + oStd + tid, small[kSmGStd + tid]); else g[oStd + tid] = small[kSmGStd + tid]; }
+        }
+
+        // ------------------------------------------------------------ loss sums
+        {
+            const float c = block_sum<kT>(loss_c, red), s = block_sum<kT>(loss_s, red), e = block_sum<kT>(loss_e, red);
+            if (tid == 0) {
+                if (sharded) { g[numel] = c * inv_bsz; g[numel + 1] = s * inv_bsz; g[numel + 2] = e * inv_bsz; }
+                else if (persistent) { acc_c += (double)(c * inv_bsz); acc_s += (double)(s * inv_bsz); acc_e += (double)(e * inv_bsz); }
+                else if (ni == 1) atomicAdd(A.loss_sums + 0, (double)(c * inv_bsz));
+                else { atomicAdd(A.loss_sums + 1, (double)(s * inv_bsz)); atomicAdd(A.loss_sums + 2, (double)(e * inv_bsz)); }
+            }
+        }
+
+        // ------------------------------------------------------------ clip_grad_norm_ + Adam.step
+        if (sharded) {
+            // ---- the gradient all-reduce, in the kernel: flags over NVLink, then ordered sums of the peers' buffers
+            px_round(A.px, 1 + ni, A.px.epoch + 1 + (uint32_t)u, A.hdr);
+            const int world = A.px.world;
+            for (int i4 = tid; i4 < (numel >> 2); i4 += kT) {
+                float4 acc = ld_relaxed_sys_v4(A.px.data[0] + px_off + 4 * i4);
+                for (int r = 1; r < world; ++r) {
+                    const float4 v = ld_relaxed_sys_v4(A.px.data[r] + px_off + 4 * i4);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                reinterpret_cast<float4*>(g_local)[i4] = acc;
+            }
+            for (int i = (numel & ~3) + tid; i < numel; i += kT) {
+                float acc = ld_relaxed_sys(A.px.data[0] + px_off + i);
+                for (int r = 1; r < world; ++r) acc += ld_relaxed_sys(A.px.data[r] + px_off + i);
+                g_local[i] = acc;
+            }
+            if (tid == 0) {
+                float c = 0.f, s = 0.f, e = 0.f;
+                for (int r = 0; r < world; ++r) {
+                    c += ld_relaxed_sys(A.px.data[r] + px_off + numel);
+                    s += ld_relaxed_sys(A.px.data[r] + px_off + numel + 1);
+                    e += ld_relaxed_sys(A.px.data[r] + px_off + numel + 2);
+                }
+                acc_c += (double)c; acc_s += (double)s; acc_e += (double)e;
+            }
+            __syncthreads();
+        }
+        if (persistent) {
+            if (tid == 0) {   // torch.optim.Adam bias corrections of this step, in double like torch
+                const double step = (double)(A.opt[ni].step + u + 1);
+                s_adam.step_size = (float)((double)A.opt[ni].lr / (1.0 - pow((double)A.opt[ni].beta1, step)));
+                s_adam.bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
+            }
+            __syncthreads();
+            apply_net<kT>(net, A.opt[ni], s_adam, g_local, numel, A.hp.clip_grad_norm, red);
+            __syncthreads();
+        } else if (A.fused_apply) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = (atomicAdd(&A.hdr->ticket[ni], 1u) == gridDim.x - 1) ? 1 : 0;
+            __syncthreads();
+            if (s_last) {   // last CTA of this net: the whole gradient is in the buffer
+                __threadfence();
+                apply_net<kT>(net, A.opt[ni], A.adam[ni], g_local, numel, A.hp.clip_grad_norm, red);
+                __syncthreads();
+                for (int i = tid; i < numel; i += kT) g_local[i] = 0.0f;
+                if (tid == 0) A.hdr->ticket[ni] = 0u;
+            }
+        }
+    }
+    if (persistent && tid == 0) {
+        if (sharded && atomicAdd(&A.hdr->pad[0], 0u) != 0u) acc_c = acc_s = acc_e = (double)nanf("");   // a peer never answered
+        const double inv = 1.0 / (double)A.update_times;
+        if (ni == 1) A.out_scalars[0] = (float)(acc_c * inv);
+        else { A.out_scalars[1] = (float)(acc_s * inv); A.out_scalars[2] = (float)(acc_e * inv); }
+    }
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+bool b200rl_update_tc_eligible(const b200rl_net* actor, const b200rl_net* critic, const b200rl_ppo_hyper* hp) {
+    for (const b200rl_net* n : {actor, critic}) {
+        if (n->num_linear != 3 || n->dims[1] != kHid || n->dims[2] != kHid || n->activation != B200RL_ACT_GELU) return false;
+        if (n->dims[0] < 1 || n->dims[0] > kMaxS || n->dims[3] < 1 || n->dims[3] > kMaxOut) return false;
+    }
+    if (critic->dims[3] != 1 || actor->dims[0] != critic->dims[0]) return false;
+    if (hp->flags & B200RL_PPO_CRITIC_MASK_MEAN) return false;   // needs the minibatch-wide mean of unmask (tutorial variant: ReLU nets anyway)
+    return true;
+}
+
+extern "C" int32_t b200rl_update_tc_supported(const b200rl_net* actor, const b200rl_net* critic, const b200rl_ppo_hyper* hyper) {
+    return (actor && critic && hyper && b200rl_update_tc_eligible(actor, critic, hyper)) ? 1 : 0;
+}
+extern "C" int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b200rl_net* critic) {
+    const int seg = ((int)b200rl_net_numel(actor) + 4 + 3 & ~3) + ((int)b200rl_net_numel(critic) + 4 + 3 & ~3);
+    return kPxStatFloats + 2 * (int64_t)seg;
+}
+
+// grid = (tiles, 2 nets).  A.update_times > 0: persistent (tiles must be 1); otherwise one minibatch.
+int b200rl_launch_update_tc(const UpdateArgs& A, int tiles, cudaStream_t stream) {
+    B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    ppo_update_tc_kernel<<<dim3((unsigned)tiles, 2), kT, kSmemBytes, stream>>>(A);
+    B200RL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -52,9 +52,9 @@ class PendulumVecEnv:
 
         self.generator = th.Generator(device=self.device)
         self.generator.manual_seed(self.seed)
-        self.theta = th.zeros(self.num_envs, dtype=th.float32, device=self.device)
-        self.theta_dot = th.zeros(self.num_envs, dtype=th.float32, device=self.device)
-        self.cur_step = th.zeros(self.num_envs, dtype=th.int32, device=self.device)
+        # ONE [3, N] block (theta, theta_dot, cur_step as int32 bits): a host loop moves the whole env state with a single copy
+        self._block = th.zeros((3, self.num_envs), dtype=th.float32, device=self.device)
+        self.theta, self.theta_dot, self.cur_step = self._block[0], self._block[1], self._block[2].view(th.int32)
         self.global_step = 0  # counts step() calls + fused steps: Philox offset of the fused kernel
         self.reset_noise: Optional[TEN] = None  # injected U[0,1) noise [T, N, 2] for parity tests
         self._reset_noise_row = 0
@@ -112,11 +112,25 @@ class PendulumVecEnv:
         self._reset_noise_row = 0
 
     def engine_state(self) -> Tuple[TEN, TEN, TEN]:
-        """Tensors the fused rollout kernel updates in place (must stay contiguous, on ``self.device``)."""
-        self.theta = self.theta.contiguous()
-        self.theta_dot = self.theta_dot.contiguous()
-        self.cur_step = self.cur_step.contiguous()
+        """Tensors the fused rollout kernel updates in place: rows of the [3, N] state block.  ``step`` / a caller may have
+        rebound the attributes to fresh tensors; those are copied back into the block first."""
+        blk = self._block
+        if self.theta.data_ptr() != blk.data_ptr():
+            blk[0].copy_(self.theta)
+            self.theta = blk[0]
+        if self.theta_dot.data_ptr() != blk[1].data_ptr():
+            blk[1].copy_(self.theta_dot)
+            self.theta_dot = blk[1]
+        if self.cur_step.data_ptr() != blk[2].data_ptr():
+            blk[2].view(th.int32).copy_(self.cur_step)
+            self.cur_step = blk[2].view(th.int32)
         return self.theta, self.theta_dot, self.cur_step
+
+    def engine_state_block(self) -> TEN:
+        """The [3, N] fp32 block behind ``engine_state()`` (row 2 = ``cur_step`` int32 bit patterns): one H2D / D2H copy
+        moves the whole env state."""
+        self.engine_state()
+        return self._block
 
 
 class PendulumEnv:

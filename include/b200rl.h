@@ -225,6 +225,44 @@ B200RL_API int b200rl_ppo_grads(const b200rl_net* actor, const b200rl_net* criti
 B200RL_API int b200rl_ppo_apply(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt,
                      b200rl_adam* critic_opt, const b200rl_ppo_hyper* hyper, void* workspace,
                      int64_t workspace_bytes, void* stream);
+/* Env-sharded update with the gradient all-reduce INSIDE the update kernel, over peer-mapped memory (NVLink): no
+ * host-issued collective at all.  Every rank calls it with ITS shard of the buffer; per minibatch every rank computes the
+ * gradient of its batch_size / world samples on tcgen05 tiles (update_tc.cu), stores it in its own exchange buffer,
+ * raises a flag in every peer's flag array, waits for the peers' flags and sums the `world` buffers in RANK ORDER with
+ * loads from the peers' memory -- the same order on every rank, so clip + Adam produce bit-identical replicas and no
+ * parameter broadcast is needed.  The advantage statistics (reference AgentPPO.py:149; b200rl_gae's stat_sums of every
+ * shard) ride on the same exchange before the first minibatch.  This is the "NCCL all-reduce of MLP gradients" of the
+ * env-sharded design fused into the compute kernel; it replaces the reference's host-pipe trajectory
+ * gather (elegantrl/train/run.py:305-320).  Nets must have the shape b200rl_update_tc_supported accepts.
+ *   data[r] / flags[r]: rank r's exchange buffer (b200rl_peer_exchange_floats floats) / flag array (B200RL_PX_FLAGS
+ *   uint32, zero-initialised once) as mapped into THIS process (symmetric allocation; data[rank] is the own one).
+ *   epoch: flags written by this call are epoch + 1 ... epoch + update_times; the caller advances it by update_times. */
+#define B200RL_MAX_PEERS 8
+#define B200RL_PX_FLAGS 64
+typedef struct b200rl_peer_exchange {
+    int32_t rank, world;
+    float* data[B200RL_MAX_PEERS];
+    uint32_t* flags[B200RL_MAX_PEERS];
+    uint32_t epoch;
+    uint32_t reserved;
+} b200rl_peer_exchange;
+B200RL_API int64_t b200rl_workspace_error_offset(void);
+B200RL_API int32_t b200rl_update_tc_supported(const b200rl_net* actor, const b200rl_net* critic, const b200rl_ppo_hyper* hyper);
+B200RL_API int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b200rl_net* critic);
+/* batch_size is the GLOBAL minibatch (a multiple of world, <= 128 * world); ids: [update_times, batch_size / world] local
+ * indices or NULL.  stat_sums: this shard's device double[4] from b200rl_gae; count_all / count_lattice as b200rl_adv_stats
+ * (global counts); adv_stats_out: device float[4], receives {mean, std, 1 / (std + 1e-5), 0}.  buffer->adv_stats is ignored
+ * (the kernel normalises with the statistics it has just reduced).  A peer that does not answer within ~2 s makes the kernel
+ * give up WITHOUT hanging the GPU and set the uint32 at b200rl_workspace_error_offset() of the workspace to 1 (the caller
+ * checks it when it reads out_scalars; results are invalid then). */
+B200RL_API int b200rl_ppo_update_sharded(const b200rl_net* actor, const b200rl_net* critic, b200rl_adam* actor_opt,
+                                         b200rl_adam* critic_opt, const b200rl_train_buffer* buffer,
+                                         const b200rl_ppo_hyper* hyper, int32_t batch_size, int32_t update_times,
+                                         const int64_t* ids, uint64_t seed, uint64_t draw_offset, const double* stat_sums,
+                                         int64_t count_all, int64_t count_lattice, float* adv_stats_out, float* out_scalars,
+                                         void* workspace, int64_t workspace_bytes, const b200rl_peer_exchange* px,
+                                         void* stream);
+
 /* out_scalars[i] = loss_sums[i] / update_times (after the caller all-reduced loss_sums if sharded). */
 B200RL_API int b200rl_loss_means(const double* loss_sums, int32_t update_times, float* out_scalars, void* stream);
 

@@ -824,3 +824,21 @@ def main_one_env():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "oneenv"):
     main_one_env()
+
+
+# ------------------------------------------------ BASELINE configs[2] / [4] state / action dims on the default 64 x 64 net
+def main_tc_shapes():
+    """Synthetic-buffer goldens for the shapes the tcgen05 update kernel (csrc/update_tc.cu) specialises on beyond Pendulum:
+    LunarLanderContinuous dims (S = 8, A = 2: layer-1 K = 24, two K steps more than Pendulum) and Hopper dims (S = 11, A = 3,
+    the kernel's largest S), both with non-trivial state_norm statistics and a batch that is not a multiple of 32."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    th.set_num_threads(1)
+    th.set_grad_enabled(True)
+    case_synthetic("synth_s8_a2_64x64", 8, 2, (64, 64), num_envs=14, horizon_len=18, seed=91,
+                   batch_size=100, repeat_times=8, norm_stats=True, lambda_entropy=0.02)
+    case_synthetic("synth_s11_a3_64x64", 11, 3, (64, 64), num_envs=9, horizon_len=20, seed=97,
+                   batch_size=72, repeat_times=6, norm_stats=True, gamma=0.98, clip_grad_norm=1.0)
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") in ("", "tcshapes"):
+    main_tc_shapes()

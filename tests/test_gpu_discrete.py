@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-@pytest.fixture(params=["cluster", "multilaunch"])
+@pytest.fixture(params=["tc", "cluster", "multilaunch"])
 def update_impl(request, monkeypatch):
     monkeypatch.setenv("B200RL_UPDATE", request.param)
     return request.param

@@ -170,7 +170,7 @@ def test_gae_sizes_against_oracle(shape, v_trace):
 
 
 # ----------------------------------------------------------------------------------------- update
-@pytest.fixture(params=["cluster", "multilaunch"])
+@pytest.fixture(params=["tc", "cluster", "multilaunch"])
 def update_impl(request, monkeypatch):
     """Both update drivers: one persistent thread-block-cluster launch for all minibatches, and one launch per
     minibatch (what large batches use)."""

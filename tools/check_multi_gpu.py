@@ -23,7 +23,8 @@ def main():
     th.cuda.set_device(local)
     dev = f"cuda:{local}"
     dist.init_process_group("nccl", device_id=th.device(dev))
-    g = gu.load("synth_s8_a2_128x64")
+    case = os.environ.get("CHECK_CASE", "synth_s8_a2_64x64")   # 64 x 64 nets: the tcgen05 update kernel + peer exchange apply
+    g = gu.load(case)
     h, n = g["buf.states"].shape[:2]
     assert n % world == 0
     shard = n // world
@@ -35,7 +36,8 @@ def main():
     global_ids = np.concatenate([(env_l[r] + r * shard) * h + t_l[r] for r in range(world)], axis=1)  # [updates, batch]
 
     keys = ("states", "actions", "logprobs", "rewards", "undones", "unmasks")
-    for mode in ("gather", "allreduce"):
+    modes = ("peer", "gather", "allreduce") if tuple(int(x) for x in g["dims"][4:]) == (64, 64) else ("gather", "allreduce")
+    for mode in modes:
         run_mode(mode, g, rank, world, local, dev, h, n, shard, lo, batch, updates, local_ids, global_ids, keys)
     dist.barrier()
     dist.destroy_process_group()
