@@ -29,12 +29,15 @@ METRIC = "env-steps/sec (rollout+GAE+update) at 65 536 envs"
 UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 17408          # actor fwd 8704 + critic fwd 8704
 HBM_BYTES_PER_ENV_STEP = 30        # 26 B trajectory + 4 B value written by the fused rollout kernel
-NCU_DRAM_BYTES_PER_LAUNCH = 196.41e6  # measured once with ncu (0.88 MB read + 195.53 MB written), profiles/r01_v5_*
+NCU_DRAM_BYTES_PER_LAUNCH = 198.11e6  # measured once with ncu (2.22 MB read + 195.89 MB written), profiles/r02_v2_rollout_ts_metrics.txt
 
 
-def workload_config(n_gpus):
-    return {"workload": "AgentPPO Pendulum-v1, 65 536 envs per GPU, horizon 128, 2x64 GELU MLP (BASELINE configs[1])",
-            "num_envs_per_gpu": NUM_ENVS, "num_envs_total": NUM_ENVS * n_gpus, "horizon_len": HORIZON,
+def workload_config(n_gpus, num_envs=None):
+    num_envs = NUM_ENVS if num_envs is None else num_envs
+    return {"workload": "AgentPPO Pendulum-v1, 65 536 envs per GPU, horizon 128, 2x64 GELU MLP (BASELINE configs[1])"
+            if num_envs == NUM_ENVS else f"AgentPPO Pendulum-v1, {num_envs} envs per GPU ({num_envs * n_gpus} in total: strong "
+            "scaling of BASELINE configs[1]), horizon 128, 2x64 GELU MLP",
+            "num_envs_per_gpu": num_envs, "num_envs_total": num_envs * n_gpus, "horizon_len": HORIZON,
             "net_dims": NET_DIMS, "batch_size": BATCH_SIZE, "repeat_times": REPEAT_TIMES,
             "update_times": int(HORIZON * REPEAT_TIMES / BATCH_SIZE), "parallelism": f"env-shard x{n_gpus}",
             "l2": "each step writes a fresh 252 MB trajectory (> 126 MB L2); no explicit flush needed",
@@ -182,8 +185,11 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    # default: BASELINE configs[1] per GPU (weak scaling).  --total-envs T: T / world envs per GPU (strong scaling study)
+    n_envs = NUM_ENVS if args.total_envs is None else args.total_envs // world
+    strong = args.total_envs is not None
 
-    env_args = {'env_name': 'Pendulum-v1', 'num_envs': NUM_ENVS, 'max_step': 200, 'state_dim': 3, 'action_dim': 1,
+    env_args = {'env_name': 'Pendulum-v1', 'num_envs': n_envs, 'max_step': 200, 'state_dim': 3, 'action_dim': 1,
                 'if_discrete': False}
     cfg = Config(AgentPPO, PendulumVecEnv, env_args)
     cfg.net_dims, cfg.batch_size, cfg.repeat_times, cfg.random_seed = NET_DIMS, BATCH_SIZE, REPEAT_TIMES, 0
@@ -191,10 +197,11 @@ def run_engine(args):
     agent = AgentPPO(NET_DIMS, 3, 1, gpu_id=local_rank, args=cfg)
     if world > 1:
         agent.enable_data_parallel()
-    env = PendulumVecEnv(num_envs=NUM_ENVS, gpu_id=local_rank, max_step=200, seed=rank)
+        agent.sharded_mode = args.sharded_mode
+    env = PendulumVecEnv(num_envs=n_envs, gpu_id=local_rank, max_step=200, seed=rank)
     agent.last_state = env.reset()[0]
     # stagger episode phases like a long-running job (otherwise every env truncates at the same step)
-    env.cur_step[:] = th.randint(0, 200, (NUM_ENVS,), device=dev, dtype=th.int32)
+    env.cur_step[:] = th.randint(0, 200, (n_envs,), device=dev, dtype=th.int32)
 
     def barrier():
         if world > 1:
@@ -206,8 +213,8 @@ def run_engine(args):
         return agent.update_net_device(list(buffer))
 
     # pinned host mirrors for the end-to-end arm: the env state block [3, N] in, last_state + env state + 3 scalars out
-    host_in = th.empty((3, NUM_ENVS), dtype=th.float32).pin_memory()
-    host_last_state = th.empty((NUM_ENVS, 3), dtype=th.float32).pin_memory()
+    host_in = th.empty((3, n_envs), dtype=th.float32).pin_memory()
+    host_last_state = th.empty((n_envs, 3), dtype=th.float32).pin_memory()
     host_in.copy_(env.engine_state_block())
 
     def cycle_e2e():
@@ -276,17 +283,17 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
 
-    env_steps = NUM_ENVS * HORIZON * args.steps * world
+    env_steps = n_envs * HORIZON * args.steps * world
     value = env_steps / (elapsed_ms * 1e-3)
     peaks = measured_peaks()
-    per_launch_env_steps = NUM_ENVS * HORIZON
-    flops = FLOP_PER_ENV_STEP * per_launch_env_steps + 8704 * NUM_ENVS  # + V(last_state)
+    per_launch_env_steps = n_envs * HORIZON
+    flops = FLOP_PER_ENV_STEP * per_launch_env_steps + 8704 * n_envs  # + V(last_state)
     achieved_tflops = flops / (rollout_ms * 1e-3) / 1e12
     hbm_gbs = HBM_BYTES_PER_ENV_STEP * per_launch_env_steps / (rollout_ms * 1e-3) / 1e9
-    roofline = {"kernel": "rollout_pendulum_tc_kernel (fused env + actor + critic + trajectory stores; 64x64 layers on tcgen05, 3xTF32)", "bound": "tensor",
+    roofline = {"kernel": "rollout_pendulum_ts_kernel (fused env + actor + critic + trajectory stores; both hidden layers on tcgen05, layer-2 A operand in tensor memory)", "bound": "tensor",
                 "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of "
-                "one `ncu --set full` capture (profiles/r01_v5_rollout_tc_metrics.txt); algorithmic 251.9e6 written, the tail "
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n_envs == 65536 else None, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of "
+                "one `ncu --set full` capture (profiles/r02_v2_rollout_ts_metrics.txt); algorithmic 251.9e6 written, the tail "
                 "of the trajectory is still in L2 when the kernel ends", "peak_source": peaks["source"], "avg_launch_ms": rollout_ms,
                 "launch_ms_min_max": [min(rollout_list), max(rollout_list)],
                 "share_of_step": rollout_ms / (elapsed_ms / args.steps),
@@ -294,10 +301,10 @@ def run_engine(args):
                 "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
                         "bytes_per_env_step": HBM_BYTES_PER_ENV_STEP}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world, n_envs), sharded_mode=(getattr(agent, "sharded_mode", None) if world > 1 else None)), "clocks": clocks,
             "e2e": {"value": env_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": 3 * NUM_ENVS * 4, "d2h_bytes_per_step": 3 * 4 + NUM_ENVS * 3 * 4 + 3 * NUM_ENVS * 4,
+                    "h2d_bytes_per_step": 3 * n_envs * 4, "d2h_bytes_per_step": 3 * 4 + n_envs * 3 * 4 + 3 * n_envs * 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline}
 
@@ -305,7 +312,7 @@ def run_engine(args):
         from oracle.cpu_port import time_cpu_cycles
         kind, time_fn, what = cpu_backend()
         threads, scores = calibrate_threads(time_fn)
-        cb = time_fn(NUM_ENVS, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, threads=threads,
+        cb = time_fn(n_envs, HORIZON, NET_DIMS, warmup=1, cycles=args.cpu_cycles, threads=threads,
                      batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
         line["cpu_baseline"] = {"value": cb["env_steps_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": kind,
                                 "sample": f"{what}: {cb['cycles']} full cycles (65 536 envs x 128 steps + update) after 1 warm-up; "
@@ -314,7 +321,7 @@ def run_engine(args):
                                           f"explore {statistics.mean(cb['explore_s']):.3f}s + update {statistics.mean(cb['update_s']):.3f}s per cycle"}
         # the same pinned op sequence as EAGER PyTorch on this very GPU (SURVEY 8(d) "stronger baseline"): what a user of the
         # reference gets with gpu_id=0 -- ~45 launches per env step, ~250 per minibatch.  Informational; ~2 s.
-        gb = time_cpu_cycles(NUM_ENVS, HORIZON, NET_DIMS, warmup=2, cycles=5, threads=threads, device=f"cuda:{local_rank}",
+        gb = time_cpu_cycles(n_envs, HORIZON, NET_DIMS, warmup=2, cycles=5, threads=threads, device=f"cuda:{local_rank}",
                              batch_size=BATCH_SIZE, repeat_times=REPEAT_TIMES)
         line["cpu_baseline"]["eager_pytorch_same_gpu"] = {
             "value": gb["env_steps_per_sec"], "unit": UNIT,
@@ -334,6 +341,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-cycles", type=int, default=4, help="CPU-baseline sample size (full cycles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-envs", type=int, default=None, help="strong-scaling study: this many envs in total, split over the GPUs")
+    ap.add_argument("--sharded-mode", default="auto", choices=["auto", "peer", "gather", "allreduce"],
+                    help="N > 1: how the env shards' gradients meet (auto = in-kernel peer-memory exchange when available)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -64,7 +64,11 @@ class RolloutArgs(C.Structure):
                 ("undones", C.c_void_p), ("unmasks", C.c_void_p), ("values", C.c_void_p),
                 ("last_state", C.c_void_p), ("last_value", C.c_void_p),
                 ("eps", C.c_void_p), ("reset_noise", C.c_void_p),
-                ("seed", C.c_uint64), ("step_offset", C.c_uint64), ("env_offset", C.c_int64)]
+                ("seed", C.c_uint64), ("step_offset", C.c_uint64), ("env_offset", C.c_int64),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+ROLLOUT_DETERMINISTIC = 1
 
 
 # symbol -> (restype, argtypes); every symbol include/b200rl.h declares (tests/test_abi.py checks the two agree)

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(512, 1) rollout_pendulum_kernel(const __grid_c
             reset_u = nz.uniform;
         }
         if (P.eps && live) e = P.eps[row + n];
+        if (P.deterministic) e = 0.0f;
         if (P.reset_noise && live) reset_u = make_float2(P.reset_noise[(row + n) * 2], P.reset_noise[(row + n) * 2 + 1]);
         const float action = __fadd_rn(__fmul_rn(e, sd), mu[0]);
         const float diff = __fsub_rn(action, mu[0]);
@@ -266,6 +267,7 @@ int b200rl_rollout_pendulum(const b200rl_rollout_args* a, void* stream_) {
     P.states = a->states; P.actions = a->actions; P.logprobs = a->logprobs; P.rewards = a->rewards;
     P.undones = a->undones; P.unmasks = a->unmasks; P.values = a->values; P.last_state = a->last_state;
     P.last_value = a->last_value; P.eps = a->eps; P.reset_noise = a->reset_noise;
+    P.deterministic = (a->flags & B200RL_ROLLOUT_DETERMINISTIC) ? 1 : 0;
     P.seed = a->seed; P.step_offset = a->step_offset; P.env_offset = a->env_offset;
 
     // 2x64 GELU actor + critic (BASELINE config 2): the tcgen05 kernel with the layer-2 A operand in tensor memory

@@ -14,6 +14,7 @@ struct RolloutParams {
     const float* eps; const float* reset_noise;
     uint64_t seed, step_offset;
     int64_t env_offset;
+    int deterministic;  // B200RL_ROLLOUT_DETERMINISTIC: zero policy noise (evaluation rollout)
     int rows_per_cta;   // rollout_ts.cu: envs per persistent CTA (set by its launcher)
 };
 

@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_pendulum_tc_kernel(const 
                 reset_u = nz.uniform;
             }
             if (P.eps && live) e = P.eps[rowbase + n];
+            if (P.deterministic) e = 0.0f;
             if (P.reset_noise && live) reset_u = make_float2(P.reset_noise[(rowbase + n) * 2], P.reset_noise[(rowbase + n) * 2 + 1]);
             const float mu = eval_net(ctx, x, lane);
             const float action = __fadd_rn(__fmul_rn(e, sd), mu);

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_ker
                         reset_u = nz.uniform;
                     }
                     if (P.eps && live) e = P.eps[rowbase + n];
+                    if (P.deterministic) e = 0.0f;
                     if (P.reset_noise && live) reset_u = make_float2(P.reset_noise[(rowbase + n) * 2], P.reset_noise[(rowbase + n) * 2 + 1]);
                     if (kEarly) store_state_row(P.states + (size_t)t * N * 3, obs0, obs1, obs2);
                     tc05::mbar_wait(&b[2], ph & 1);

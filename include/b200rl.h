@@ -131,7 +131,12 @@ typedef struct b200rl_rollout_args {
     uint64_t seed;                        /* Philox key */
     uint64_t step_offset;                 /* global step index of t = 0 (Philox counter) */
     int64_t env_offset;                   /* global env index of local env 0 (Philox counter, multi-GPU shards) */
+    int32_t flags;                        /* B200RL_ROLLOUT_*: 0 = exploration (ActorPPO.get_action) */
+    int32_t reserved;
 } b200rl_rollout_args;
+/* Deterministic policy: the env receives tanh(mean) = ActorPPO.forward (AgentPPO.py:363-366), the policy noise is zero --
+ * the evaluation rollout of the reference's Evaluator (elegantrl/train/evaluator.py:200-216: `action = actor(state)`). */
+#define B200RL_ROLLOUT_DETERMINISTIC 1
 
 B200RL_API const char* b200rl_version(void);
 B200RL_API const char* b200rl_last_error(void);

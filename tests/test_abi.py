@@ -38,10 +38,11 @@ def test_struct_layouts_match_c():
     #include <stddef.h>
     #include "b200rl.h"
     int main(void) {
-        printf("%zu %zu %zu %zu %zu\n", sizeof(b200rl_net), sizeof(b200rl_adam), sizeof(b200rl_ppo_hyper),
-               sizeof(b200rl_train_buffer), sizeof(b200rl_rollout_args));
-        printf("%zu %zu %zu %zu %zu\n", offsetof(b200rl_net, weight), offsetof(b200rl_net, action_std_log),
-               offsetof(b200rl_adam, lr), offsetof(b200rl_adam, step), offsetof(b200rl_rollout_args, seed));
+        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(b200rl_net), sizeof(b200rl_adam), sizeof(b200rl_ppo_hyper),
+               sizeof(b200rl_train_buffer), sizeof(b200rl_rollout_args), sizeof(b200rl_peer_exchange));
+        printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(b200rl_net, weight), offsetof(b200rl_net, action_std_log),
+               offsetof(b200rl_adam, lr), offsetof(b200rl_adam, step), offsetof(b200rl_rollout_args, seed),
+               offsetof(b200rl_rollout_args, flags), offsetof(b200rl_peer_exchange, epoch));
         return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -49,12 +50,12 @@ def test_struct_layouts_match_c():
         open(src, "w").write(probe)
         subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), src, "-o", exe], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
-    sizes = [int(x) for x in out[:5]]
-    offs = [int(x) for x in out[5:]]
+    sizes = [int(x) for x in out[:6]]
+    offs = [int(x) for x in out[6:]]
     assert sizes == [C.sizeof(_lib.Net), C.sizeof(_lib.Adam), C.sizeof(_lib.PPOHyper), C.sizeof(_lib.TrainBuffer),
-                     C.sizeof(_lib.RolloutArgs)]
+                     C.sizeof(_lib.RolloutArgs), C.sizeof(_lib.PeerExchange)]
     assert offs == [_lib.Net.weight.offset, _lib.Net.action_std_log.offset, _lib.Adam.lr.offset, _lib.Adam.step.offset,
-                    _lib.RolloutArgs.seed.offset]
+                    _lib.RolloutArgs.seed.offset, _lib.RolloutArgs.flags.offset, _lib.PeerExchange.epoch.offset]
 
 
 def test_argument_validation_reports_errors():
