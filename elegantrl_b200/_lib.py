@@ -55,6 +55,34 @@ class PeerExchange(C.Structure):
                 ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+SAC_MAX_ENSEMBLES, MAX_GROUP_TENSORS = 8, 64
+
+
+class SacActor(C.Structure):
+    _fields_ = [("net_s", Net), ("net_a", Net)]
+
+
+class SacCritic(C.Structure):
+    _fields_ = [("encoder", Net), ("num_ensembles", C.c_int32), ("reserved", C.c_int32), ("decoder", Net * SAC_MAX_ENSEMBLES)]
+
+
+class ParamGroup(C.Structure):
+    _fields_ = [("num_tensors", C.c_int32), ("reserved", C.c_int32), ("param", C.c_void_p * MAX_GROUP_TENSORS),
+                ("exp_avg", C.c_void_p * MAX_GROUP_TENSORS), ("exp_avg_sq", C.c_void_p * MAX_GROUP_TENSORS),
+                ("numel", C.c_int32 * MAX_GROUP_TENSORS), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("step", C.c_int64)]
+
+
+class ReplayBufferDesc(C.Structure):
+    _fields_ = [("states", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p), ("undones", C.c_void_p),
+                ("unmasks", C.c_void_p), ("max_size", C.c_int32), ("num_seqs", C.c_int32), ("state_dim", C.c_int32),
+                ("action_dim", C.c_int32)]
+
+
+class SacHyper(C.Structure):
+    _fields_ = [("gamma", C.c_float), ("soft_update_tau", C.c_float), ("clip_grad_norm", C.c_float), ("target_entropy", C.c_float)]
+
+
 class RolloutArgs(C.Structure):
     _fields_ = [("actor", C.POINTER(Net)), ("critic", C.POINTER(Net)),
                 ("num_envs", C.c_int32), ("horizon_len", C.c_int32), ("max_step", C.c_int32),
@@ -101,6 +129,15 @@ SIGNATURES = {
     "b200rl_ppo_apply": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.POINTER(Adam), C.POINTER(Adam),
                                    C.POINTER(PPOHyper), C.c_void_p, C.c_int64, C.c_void_p]),
     "b200rl_loss_means": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200rl_replay_append": (C.c_int, [C.POINTER(ReplayBufferDesc), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200rl_sac_policy_step": (C.c_int, [C.POINTER(SacActor), C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64,
+                                         C.c_void_p, C.c_void_p]),
+    "b200rl_sac_workspace_bytes": (C.c_int64, [C.POINTER(SacActor), C.POINTER(SacCritic), C.c_int32]),
+    "b200rl_sac_update": (C.c_int, [C.POINTER(SacActor), C.POINTER(SacCritic), C.POINTER(SacCritic), C.POINTER(ParamGroup),
+                                    C.POINTER(ParamGroup), C.POINTER(ParamGroup), C.POINTER(ReplayBufferDesc), C.c_int32,
+                                    C.POINTER(SacHyper), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                    C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200rl_workspace_error_offset": (C.c_int64, []),
     "b200rl_update_tc_supported": (C.c_int32, [C.POINTER(Net), C.POINTER(Net), C.POINTER(PPOHyper)]),
     "b200rl_peer_exchange_floats": (C.c_int64, [C.POINTER(Net), C.POINTER(Net)]),

@@ -1,6 +1,7 @@
 from .AgentPPO import AgentA2C, AgentDiscreteA2C, AgentDiscretePPO, AgentPPO
-from .nets import ActorDiscretePPO, ActorPPO, CriticPPO
+from .AgentSAC import AgentSAC
+from .nets import ActorDiscretePPO, ActorPPO, ActorSAC, CriticEnsemble, CriticPPO
 from . import helloworld
 
-__all__ = ["AgentPPO", "AgentDiscretePPO", "AgentA2C", "AgentDiscreteA2C", "ActorPPO", "ActorDiscretePPO", "CriticPPO",
-           "helloworld"]
+__all__ = ["AgentPPO", "AgentDiscretePPO", "AgentA2C", "AgentDiscreteA2C", "AgentSAC", "ActorPPO", "ActorDiscretePPO", "CriticPPO",
+           "ActorSAC", "CriticEnsemble", "helloworld"]

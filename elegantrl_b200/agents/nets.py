@@ -122,3 +122,48 @@ class ActorDiscretePPO(ActorPPO):
     @staticmethod
     def convert_action_for_env(action: TEN) -> TEN:
         return action.long()
+
+
+# ------------------------------------------------------------------------------------------ off-policy (SAC) containers
+class ActorSAC(nn.Module):
+    """Container with the reference's attribute names / state_dict keys (``elegantrl/agents/AgentSAC.py:167-198``):
+    ``net_s`` = build_mlp([S, *net_dims], if_raw_out=False) -- an activation after EVERY Linear -- and ``net_a`` = one Linear
+    producing [mean | log_std].  ``forward`` (what the Evaluator calls) is the tanh of the mean."""
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int):
+        super().__init__()
+        self.state_dim, self.action_dim = state_dim, action_dim
+        layers = []
+        for d_in, d_out in zip([state_dim, *net_dims][:-1], [state_dim, *net_dims][1:]):
+            layers += [nn.Linear(d_in, d_out), nn.GELU()]
+        self.net_s = nn.Sequential(*layers)
+        self.net_a = nn.Sequential(nn.Linear(net_dims[-1], action_dim * 2))
+        _init_output_layer(self.net_a[-1], std=0.1)
+
+    def forward(self, state: TEN) -> TEN:
+        return self.net_a(self.net_s(state))[:, :self.action_dim].tanh()
+
+
+class CriticEnsemble(nn.Module):
+    """``elegantrl/agents/AgentSAC.py:244-259``: ``encoder_sa`` (one raw Linear of (state, action)) feeding
+    ``decoder_q00`` ... (``build_mlp([*net_dims, 1])`` each).  ``forward`` = mean over the ensemble, as ``CriticBase.forward``."""
+
+    def __init__(self, net_dims, state_dim: int, action_dim: int, num_ensembles: int = 4):
+        super().__init__()
+        self.state_dim, self.action_dim, self.num_ensembles = state_dim, action_dim, num_ensembles
+        self.encoder_sa = nn.Sequential(nn.Linear(state_dim + action_dim, net_dims[0]))
+        for i in range(num_ensembles):
+            decoder = make_mlp([*net_dims, 1])
+            _init_output_layer(decoder[-1], std=0.5)
+            setattr(self, f"decoder_q{i:02}", decoder)
+
+    @property
+    def decoder_qs(self):
+        return [getattr(self, f"decoder_q{i:02}") for i in range(self.num_ensembles)]
+
+    def get_q_values(self, state: TEN, action: TEN) -> TEN:
+        enc = self.encoder_sa(th.cat((state, action), dim=1))
+        return th.cat([dec(enc) for dec in self.decoder_qs], dim=-1)
+
+    def forward(self, state: TEN, action: TEN) -> TEN:
+        return self.get_q_values(state, action).mean(dim=-1, keepdim=True)

@@ -1,3 +1,4 @@
+from .replay_buffer import ReplayBuffer
 from .run import train_agent
 
-__all__ = ["train_agent"]
+__all__ = ["ReplayBuffer", "train_agent"]

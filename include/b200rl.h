@@ -271,6 +271,83 @@ B200RL_API int b200rl_ppo_update_sharded(const b200rl_net* actor, const b200rl_n
 /* out_scalars[i] = loss_sums[i] / update_times (after the caller all-reduced loss_sums if sharded). */
 B200RL_API int b200rl_loss_means(const double* loss_sums, int32_t update_times, float* out_scalars, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Off-policy path (BASELINE configs[3]): ReplayBuffer + AgentSAC.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define B200RL_SAC_MAX_ENSEMBLES 8
+#define B200RL_MAX_GROUP_TENSORS 64
+
+/* ActorSAC (elegantrl/agents/AgentSAC.py:167-198): state encoder + one Linear producing [mean | log_std]. */
+typedef struct b200rl_sac_actor {
+    b200rl_net net_s;                     /* build_mlp([S, *net_dims], if_raw_out=False): activation after EVERY Linear */
+    b200rl_net net_a;                     /* one Linear net_dims[-1] -> 2 * action_dim */
+} b200rl_sac_actor;
+
+/* CriticEnsemble (AgentSAC.py:244-259): shared raw Linear encoder of (state, action), E decoder MLPs -> Q [B, E]. */
+typedef struct b200rl_sac_critic {
+    b200rl_net encoder;                   /* one Linear (S + A) -> net_dims[0], no activation */
+    int32_t num_ensembles;                /* 1..B200RL_SAC_MAX_ENSEMBLES */
+    int32_t reserved;
+    b200rl_net decoder[B200RL_SAC_MAX_ENSEMBLES];   /* build_mlp([*net_dims, 1]) each */
+} b200rl_sac_critic;
+
+/* One torch.optim.Adam over a flat parameter list (optimizer order), stepped by AgentBase.optimizer_backward
+ * (elegantrl/agents/AgentBase.py:239-248: clip_grad_norm_ over the whole list, then Adam.step). */
+typedef struct b200rl_param_group {
+    int32_t num_tensors;
+    int32_t reserved;
+    float* param[B200RL_MAX_GROUP_TENSORS];
+    float* exp_avg[B200RL_MAX_GROUP_TENSORS];
+    float* exp_avg_sq[B200RL_MAX_GROUP_TENSORS];
+    int32_t numel[B200RL_MAX_GROUP_TENSORS];
+    float lr, beta1, beta2, eps;
+    int64_t step;                         /* steps already taken; advanced by the engine (host field) */
+} b200rl_param_group;
+
+/* ReplayBuffer storage (elegantrl/train/replay_buffer.py:55-59): time-major rings [max_size, num_seqs, ...], all fp32
+ * (undones / unmasks are float32 in the reference).  `max_size` is the TIME length. */
+typedef struct b200rl_replay_buffer {
+    float* states;                        /* [max_size, num_seqs, state_dim] */
+    float* actions;                       /* [max_size, num_seqs, action_dim] (tanh'ed actions, AgentSAC.py:176-182) */
+    float* rewards;                       /* [max_size, num_seqs] */
+    float* undones;                       /* [max_size, num_seqs] */
+    float* unmasks;                       /* [max_size, num_seqs] */
+    int32_t max_size, num_seqs, state_dim, action_dim;
+} b200rl_replay_buffer;
+
+typedef struct b200rl_sac_hyper {
+    float gamma;                          /* Config.gamma */
+    float soft_update_tau;                /* Config.soft_update_tau (AgentBase.py:270-278) */
+    float clip_grad_norm;                 /* Config.clip_grad_norm, applied per optimizer */
+    float target_entropy;                 /* AgentSAC: +log(action_dim) (:31) */
+} b200rl_sac_hyper;
+
+/* ReplayBuffer.update (replay_buffer.py:78-118): rows [p, p + rows) (mod max_size) of the five rings <- one rollout
+ * (states [rows, N, S], actions [rows, N, A], rewards [rows, N] fp32; undones / unmasks [rows, N] torch.bool, converted to
+ * the buffer's float32).  The pointer arithmetic (p, cur_size, if_full) stays with the caller, as in the reference. */
+B200RL_API int b200rl_replay_append(const b200rl_replay_buffer* buffer, int32_t p, int32_t rows, const float* states,
+                                    const float* actions, const float* rewards, const uint8_t* undones,
+                                    const uint8_t* unmasks, void* stream);
+/* ActorSAC.get_action (AgentSAC.py:176-182): action = tanh(mean + clamp(log_std, -16, 2).exp() * eps) for `rows` states.
+ * eps [rows, A] injected N(0,1) or NULL (Philox keyed by seed / step / env_offset + row). */
+B200RL_API int b200rl_sac_policy_step(const b200rl_sac_actor* actor, const float* state, int64_t rows, const float* eps,
+                                      uint64_t seed, uint64_t step, int64_t env_offset, float* action, void* stream);
+B200RL_API int64_t b200rl_sac_workspace_bytes(const b200rl_sac_actor* actor, const b200rl_sac_critic* critic, int32_t batch_size);
+/* update_times x AgentSAC.update_objectives (AgentSAC.py:42-86; no PER, lambda_fit_cum_r = 0): ReplayBuffer.sample
+ * (:120-134, next state = next time row), q_label from the actor and the target ensemble, critic step, soft target update,
+ * temperature step, actor step through the target ensemble -- including the reference's quirks (log-prob at the mean,
+ * 1.000001 - tanh^2, alpha taken after its Adam step and before the clamp).  cur_size: valid time rows of the buffer.
+ * ids: device int64 [update_times, batch_size] in [0, (cur_size - 1) * num_seqs) or NULL (Philox); eps_next / eps_pg: the two
+ * rsample draws per update, device fp32 [update_times, batch_size, A], or NULL (Philox).  alpha_log: device fp32 [1] with
+ * its one-tensor Adam group.  out_scalars (device float[2]) = means of (obj_critic, obj_actor) (AgentBase.py:172-189). */
+B200RL_API int b200rl_sac_update(const b200rl_sac_actor* actor, const b200rl_sac_critic* critic,
+                                 const b200rl_sac_critic* critic_target, b200rl_param_group* actor_group,
+                                 b200rl_param_group* critic_group, b200rl_param_group* alpha_group,
+                                 const b200rl_replay_buffer* buffer, int32_t cur_size, const b200rl_sac_hyper* hyper,
+                                 int32_t batch_size, int32_t update_times, const int64_t* ids, const float* eps_next,
+                                 const float* eps_pg, uint64_t seed, uint64_t draw_offset, float* out_scalars,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
