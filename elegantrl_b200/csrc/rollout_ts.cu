@@ -41,7 +41,7 @@ constexpr int kWorkerWarps = 14, kIssuerWarps = kTiles;
 //   2  issuer warps on the two schedulers that host only 3 worker warps (warp ids 14, 15, 18, 19; 16 and 17 stay idle)
 //   4  one arrival per 32 hidden units instead of per 16 (half the arrivals / issuer wake-ups; 8 UMMAs per wake-up)
 //   8  the state row of step t is stored while the actor's last UMMAs run (it is known at the start of the step)
-constexpr int kDefaultVariant = 0;
+constexpr int kDefaultVariant = 2;   // profiles/r02_v3_rollout_ts_variants.log
 constexpr int kVarPrefetch = 1, kVarIssuerPlace = 2, kVarArrive2 = 4, kVarEarlyStore = 8;
 template <int V> constexpr int warps_of() { return (V & kVarIssuerPlace) ? 20 : kWorkerWarps + kIssuerWarps; }
 constexpr int kTileCols = 128;   // TMEM columns per tile: X [0, 64) + D [64, 128)

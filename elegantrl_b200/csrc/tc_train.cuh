@@ -8,10 +8,17 @@
 //   * "K-major image" of a weight W [R][K] exactly as nn.Linear stores it: offset(r, k) = (r/8)*(K/4)*128 + (k/4)*128 + (r%8)*16
 //     + (k%4)*4.  Forward reads it K-major (B = W, D = A W^T); the backward data gradient reads THE SAME bytes as the MN-major
 //     operand W^T (D = dZ W) by swapping the two strides of the descriptor -- no transposed copy.
-//   * "row-written image" of a per-sample matrix Q [128 samples][C]: offset(b, c) = (c/4)*2048 + b*16 + (c%4)*4, i.e. sample b
-//     stores its own row with 128-bit stores (a warp covers 512 contiguous bytes per 4-column group: conflict-free).  Read as
-//     an MN-major operand with MN = column, K = sample: this is how the weight gradients  dW = dZ^T X  (a contraction over
-//     the SAMPLE axis) reach the tensor core without any transposition through shared memory.
+//   * "row-written image" of a per-sample matrix Q [128 samples][C]: sample b stores its own row with 128-bit stores; the
+//     tensor core reads it as an MN-major operand with MN = column, K = sample -- this is how the weight gradients
+//     dW = dZ^T X (a contraction over the SAMPLE axis) reach the tensor core without a transposition through shared memory.
+//     MN-major kind::tf32 operands exist in ONE layout only, SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major
+//     tf32 operands, SW128_32B is the only available smem layout"; measured: with any other layout type the UMMA writes
+//     nothing, profiles/r02_v4_mn_major_probe.log).  Atom = 32 columns (128 B) x 4 samples at 128 B, Swizzle<2,5,2> in bits:
+//       offset(b, c) = (c/32)*LBO + (b/4)*512 + (b%4)*128 + (c%32)*4,   byte bits [2,4) ^= byte bits [4,6)
+//     i.e. inside every 16-byte unit u the four elements are permuted by e -> e ^ (u & 3): a compile-time shuffle of the
+//     registers a thread stores.  LBO (between 32-column groups) = 128 samples / 4 * 512 = 16 KB.
+//   * the backward image of W2 (for dH1 = dZ2 W2: B [n = input][K = output]) is the same layout with MN = input feature,
+//     K = output feature: offset(j, k) = (k/32)*8192 + (j/4)*512 + (j%4)*128 + (k%32)*4, swizzled.
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
@@ -20,9 +27,11 @@ namespace tctrain {
 
 constexpr int kHid = 64, kTile = 128;
 constexpr int kWPlaneBytes = kHid * kHid * 4;        // one tf32 plane of a 64 x 64 weight, K-major image: 16 KB
-constexpr int kGAPlaneBytes = kHid * kTile * 4;      // row-written image [128][64]: 32 KB
-constexpr int kGB2PlaneBytes = 72 * kTile * 4;       // row-written image [128][64 + 8]: 36 KB
-constexpr uint32_t kRowGroupStride = kTile * 16;     // bytes between 4-column groups of a row-written image
+constexpr uint32_t kMnSBO = 512;                      // bytes between 4-deep K groups of an MN-major (SW128_32B) image
+constexpr uint32_t kRowLBO = kTile / 4 * kMnSBO;      // bytes between 32-column groups of a row-written image: 16 KB
+constexpr uint32_t kWbLBO = kHid / 4 * kMnSBO;        // ... of the backward weight image (K = 64 output features): 8 KB
+constexpr int kGroupPlaneBytes = (int)kRowLBO;        // one 32-column group of a row-written image
+constexpr int kGAPlaneBytes = 2 * kGroupPlaneBytes;   // row-written image [128][64]: 32 KB
 
 // ---- exact-erf GELU and its derivative from ONE evaluation of q = Phi(-|x|) (tools/fit_gelu.py; max abs error 5.8e-7 / 1e-6)
 //   GELU(x) = max(x, 0) - |x| q,   GELU'(x) = Phi(x) + x phi(x),  Phi(x) = x >= 0 ? 1 - q : q,  phi(x) = exp(-x^2/2) / sqrt(2 pi)
@@ -77,6 +86,17 @@ DEV void stage_w_planes(const float* W, unsigned char* hi, unsigned char* lo, in
         *reinterpret_cast<float*>(lo + off) = w - h;
     }
 }
+DEV uint32_t mn_swizzle(uint32_t byte_off) { return byte_off ^ (((byte_off >> 4) & 3u) << 2); }
+// ... and its backward image (MN = input feature k, K = output feature j), hi / lo planes
+DEV void stage_w_planes_backward(const float* W, unsigned char* hi, unsigned char* lo, int tid, int nthreads) {
+    for (int i = tid; i < kHid * kHid; i += nthreads) {
+        const int j = i >> 6, k = i & 63;
+        const float w = __ldcg(W + i), h = tc05::tf32_hi(w);
+        const uint32_t off = mn_swizzle((uint32_t)(k >> 5) * kWbLBO + (uint32_t)(j >> 2) * kMnSBO + (uint32_t)(j & 3) * 128 + (uint32_t)(k & 31) * 4);
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = w - h;
+    }
+}
 // 16 consecutive columns of this thread's row -> hi / lo planes in tensor memory (two tcgen05.st; caller waits)
 DEV void store_hi_lo_tmem(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
     uint32_t h[16], l[16];
@@ -92,16 +112,30 @@ DEV void store_hi_lo_tmem(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)
 DEV void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// NV consecutive columns [col0, col0 + NV) (col0 % 4 == 0) of sample b's row -> hi / lo row-written images
+// NV consecutive columns [col0, col0 + NV) of sample b's row -> hi / lo row-written images (col0 % 16 == 0 or NV == 8 with
+// col0 % 8 == 0; the NV columns stay inside one 32-column group).  Unit u = 16-byte unit inside the 128-byte row; its four
+// elements are stored permuted by e -> e ^ (u & 3) (the layout's swizzle), a compile-time choice of registers.
 template <int NV>
 DEV void store_hi_lo_rows_n(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[NV]) {
-    const uint32_t hi0 = tc05::smem_u32(hi_plane) + (uint32_t)(col0 >> 2) * kRowGroupStride + (uint32_t)b * 16;
-    const uint32_t lo0 = tc05::smem_u32(lo_plane) + (uint32_t)(col0 >> 2) * kRowGroupStride + (uint32_t)b * 16;
+    const uint32_t row = (uint32_t)(col0 >> 5) * kRowLBO + (uint32_t)(b >> 2) * kMnSBO + (uint32_t)(b & 3) * 128;
+    const uint32_t u0 = (uint32_t)(col0 & 31) >> 2;   // NV / 4 consecutive units; u0 % (NV / 4) == 0, so (u0 + q) & 3 == q & 3 ... for NV = 16; NV = 8: (u0 & 2) | q
+    const uint32_t hi0 = tc05::smem_u32(hi_plane) + row + u0 * 16, lo0 = tc05::smem_u32(lo_plane) + row + u0 * 16;
 #pragma unroll
     for (int q = 0; q < NV / 4; ++q) {
-        const float h0 = tc05::tf32_hi(v[4 * q]), h1 = tc05::tf32_hi(v[4 * q + 1]), h2 = tc05::tf32_hi(v[4 * q + 2]), h3 = tc05::tf32_hi(v[4 * q + 3]);
-        st_shared_v4(hi0 + q * kRowGroupStride, h0, h1, h2, h3);
-        st_shared_v4(lo0 + q * kRowGroupStride, v[4 * q] - h0, v[4 * q + 1] - h1, v[4 * q + 2] - h2, v[4 * q + 3] - h3);
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { h[e] = tc05::tf32_hi(v[4 * q + e]); l[e] = v[4 * q + e] - h[e]; }
+        // position p of the unit holds element p ^ s, s = (u0 + q) & 3: s is only known at run time through u0's bit 1 when
+        // NV == 8 (u0 in {0, 2, 4, 6}); resolve it with one uniform branch on (u0 & 2)
+        const int s_lo = q & 3;
+        if (NV == 16 || !(u0 & 2)) {
+            st_shared_v4(hi0 + q * 16, h[0 ^ s_lo], h[1 ^ s_lo], h[2 ^ s_lo], h[3 ^ s_lo]);
+            st_shared_v4(lo0 + q * 16, l[0 ^ s_lo], l[1 ^ s_lo], l[2 ^ s_lo], l[3 ^ s_lo]);
+        } else {
+            const int s2 = s_lo ^ 2;
+            st_shared_v4(hi0 + q * 16, h[0 ^ s2], h[1 ^ s2], h[2 ^ s2], h[3 ^ s2]);
+            st_shared_v4(lo0 + q * 16, l[0 ^ s2], l[1 ^ s2], l[2 ^ s2], l[3 ^ s2]);
+        }
     }
 }
 DEV void store_hi_lo_rows(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[16]) {
@@ -111,38 +145,47 @@ DEV void store_hi_lo_rows8(unsigned char* hi_plane, unsigned char* lo_plane, int
     store_hi_lo_rows_n<8>(hi_plane, lo_plane, b, col0, v);
 }
 
+// MN-major tf32 descriptor: layout type SWIZZLE_128B_BASE32B; LBO = stride between 32-element MN groups, SBO = stride
+// between 4-deep K groups (cute make_umma_desc<Major::MN>, swizzled branch)
+DEV uint64_t make_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return tc05::make_smem_desc_ex(smem_addr, lbo_bytes, kMnSBO) | ((uint64_t)1 << 61);
+}
+
 // ---- issuer side (ONE thread)
-// D[128 x 64] (+)= A * W^T (transposed = false) or A * W (transposed = true), K = 64: A = hi / lo planes in tensor memory
-// (64 columns each, lane = sample), W = hi / lo K-major images of a 64 x 64 weight.  24 UMMAs 128 x 64 x 8.
-DEV void issue_linear_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t w_hi, uint32_t w_lo, bool transposed,
-                         bool accumulate) {
-    const uint32_t idesc = tc05::make_idesc_tf32_ex(kTile, kHid, false, transposed);
+// D[128 x 64] (+)= A * W^T: A = hi / lo planes in tensor memory (64 columns each, lane = sample), W = hi / lo K-major
+// images of a 64 x 64 weight.  24 UMMAs 128 x 64 x 8.
+DEV void issue_linear_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t w_hi, uint32_t w_lo, bool accumulate) {
+    const uint32_t idesc = tc05::make_idesc_tf32_ex(kTile, kHid, false, false);
     const uint32_t sbo_k = (kHid / 4) * 128;   // 2048: stride between 8-row groups of the K-major image
 #pragma unroll 1
     for (int ks = 0; ks < kHid / 8; ++ks) {
-        uint64_t b_hi, b_lo;
-        if (!transposed) {   // K = input feature: two 16-byte chunks per step
-            b_hi = tc05::make_smem_desc_ex(w_hi + ks * 256, 128, sbo_k);
-            b_lo = tc05::make_smem_desc_ex(w_lo + ks * 256, 128, sbo_k);
-        } else {             // K = output feature = image row: one 8-row group per step; MN groups are the 16-byte K chunks
-            b_hi = tc05::make_smem_desc_ex(w_hi + ks * sbo_k, sbo_k, 128);
-            b_lo = tc05::make_smem_desc_ex(w_lo + ks * sbo_k, sbo_k, 128);
-        }
+        const uint64_t b_hi = tc05::make_smem_desc_ex(w_hi + ks * 256, 128, sbo_k);   // K = input feature: two 16-byte chunks per step
+        const uint64_t b_lo = tc05::make_smem_desc_ex(w_lo + ks * 256, 128, sbo_k);
         tc05::mma_tf32_ts(tmem_d, tmem_a_hi + 8 * ks, b_hi, idesc, accumulate || ks > 0);
         tc05::mma_tf32_ts(tmem_d, tmem_a_lo + 8 * ks, b_hi, idesc, true);
         tc05::mma_tf32_ts(tmem_d, tmem_a_hi + 8 * ks, b_lo, idesc, true);
     }
 }
-// D[64 x N] = G^T * Q over the 128 samples: G [128][64] and Q [128][N] as row-written hi / lo images (lo plane = hi plane
-// address + plane bytes).  48 UMMAs 64 x N x 8; accumulator rows at TMEM lanes (m % 16) + 32 * (m / 16).
+// D[128 x 64] = A * W (the data gradient): the B operand is the backward image of W (MN-major: MN = input feature)
+DEV void issue_linear_ts_backward(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t wb_hi, uint32_t wb_lo) {
+    const uint32_t idesc = tc05::make_idesc_tf32_ex(kTile, kHid, false, true);
+#pragma unroll 1
+    for (int ks = 0; ks < kHid / 8; ++ks) {      // K = output feature: two 4-deep K groups per step
+        const uint64_t b_hi = make_mn_desc(wb_hi + ks * 2 * kMnSBO, kWbLBO), b_lo = make_mn_desc(wb_lo + ks * 2 * kMnSBO, kWbLBO);
+        tc05::mma_tf32_ts(tmem_d, tmem_a_hi + 8 * ks, b_hi, idesc, ks > 0);
+        tc05::mma_tf32_ts(tmem_d, tmem_a_lo + 8 * ks, b_hi, idesc, true);
+        tc05::mma_tf32_ts(tmem_d, tmem_a_hi + 8 * ks, b_lo, idesc, true);
+    }
+}
+// D[64 x N] = G^T * Q over the 128 samples: G [128][64] and Q [128][N <= 32] as row-written hi / lo images (lo plane = hi
+// plane address + plane bytes).  48 UMMAs 64 x N x 8; accumulator rows at TMEM lanes (m % 16) + 32 * (m / 16).
 DEV void issue_weight_grad(uint32_t tmem_d, uint32_t ga, uint32_t ga_plane_bytes, uint32_t gb, uint32_t gb_plane_bytes, int N) {
     const uint32_t idesc = tc05::make_idesc_tf32_ex(64, N, true, true);
 #pragma unroll 1
     for (int ks = 0; ks < kTile / 8; ++ks) {
-        const uint64_t a_hi = tc05::make_smem_desc_ex(ga + ks * 128, 128, kRowGroupStride);
-        const uint64_t a_lo = tc05::make_smem_desc_ex(ga + ga_plane_bytes + ks * 128, 128, kRowGroupStride);
-        const uint64_t b_hi = tc05::make_smem_desc_ex(gb + ks * 128, 128, kRowGroupStride);
-        const uint64_t b_lo = tc05::make_smem_desc_ex(gb + gb_plane_bytes + ks * 128, 128, kRowGroupStride);
+        const uint32_t step = ks * 2 * kMnSBO;
+        const uint64_t a_hi = make_mn_desc(ga + step, kRowLBO), a_lo = make_mn_desc(ga + ga_plane_bytes + step, kRowLBO);
+        const uint64_t b_hi = make_mn_desc(gb + step, kRowLBO), b_lo = make_mn_desc(gb + gb_plane_bytes + step, kRowLBO);
         tc05::mma_tf32(tmem_d, a_hi, b_hi, idesc, ks > 0);
         tc05::mma_tf32(tmem_d, a_lo, b_hi, idesc, true);
         tc05::mma_tf32(tmem_d, a_hi, b_lo, idesc, true);

@@ -6,10 +6,10 @@
 // One CTA = one tile of 128 sampled transitions of ONE net (grid = tiles x 2), thread = sample = TMEM lane.  Every dense
 // contraction of the forward AND backward pass is a tcgen05 tile (3xTF32: hi / lo planes, fp32 accumulate in TMEM):
 //   L1   Z1 [128 x 64] = x~ B1^T            x~ = [x_hi, 1, x_lo, 0] (bias folded), K = round_up(2 S + 1, 8)      SS
-//   L2   Z2 [128 x 64] = b2 + H1 W2^T       H1 = GELU(Z1) as hi / lo planes in tensor memory                     TS
-//   dH1  [128 x 64]    = dZ2 W2             dZ2 planes in tensor memory; W2's forward image read MN-major        TS
-//   G2   [ 64 x 72]    = dZ2^T [H1 | 1]     = [dW2 | db2]: contraction over the SAMPLES; both operands are
-//   G1   [ 64 x N1]    = dZ1^T [X  | 1]     = [dW1 | db1]  row-written shared-memory images read MN-major         SS
+//   L2   Z2 [128 x 64] = H1 W2^T            H1 = GELU(Z1) as hi / lo planes in tensor memory (b2 added on read)   TS
+//   dH1  [128 x 64]    = dZ2 W2             dZ2 planes in tensor memory; W2's backward (MN-major) image          TS
+//   G2   [ 64 x 64]    = dZ2^T H1           = dW2, in two passes of 32 columns: contraction over the SAMPLES;
+//   G1   [ 64 x N1]    = dZ1^T [X  | 1]     = [dW1 | db1]  both operands are row-written MN-major images          SS
 // GELU / GELU', the head (64 -> OUT), the PPO loss and its derivative run on CUDA cores, thread = sample; the head's
 // weight gradient is reduced with shuffles.  Gradients go to the flat buffer of the workspace; clip + Adam is the shared
 // apply_net (update_common.cuh).  With one tile per net (batch_size <= 128: the Config default) the kernel is PERSISTENT:
@@ -28,26 +28,24 @@ constexpr int kT = 128;
 constexpr int kMaxS = 11, kMaxOut = 8, kK1Max = 24;
 
 // ---- dynamic shared memory map (bytes)
-constexpr int kOffW2 = 0;                                      // W2 hi / lo K-major images
-constexpr int kOffGA = kOffW2 + 2 * kWPlaneBytes;              // dZ rows (hi / lo): A operand of G2, then of G1
-constexpr int kOffGB2 = kOffGA + 2 * kGAPlaneBytes;            // [H1 | 1 | 0] rows (hi / lo)
-constexpr int kGB1PlaneBytes = 16 * kT * 4;
-constexpr int kOffGB1 = kOffGB2 + 2 * kGB2PlaneBytes;          // [X | 1 | 0] rows (hi / lo)
+constexpr int kOffW2 = 0;                                      // W2 hi / lo K-major images (forward)
+constexpr int kOffWB = kOffW2 + 2 * kWPlaneBytes;              // W2 hi / lo backward images (MN-major)
+constexpr int kOffGA = kOffWB + 2 * kWPlaneBytes;              // dZ rows (hi / lo): A operand of G2, then of G1
+constexpr int kOffGB = kOffGA + 2 * kGAPlaneBytes;             // ONE 32-column group (hi / lo): H1[:, 0:32], H1[:, 32:64], [X | 1]
 constexpr int kA1Bytes = kT * kK1Max * 4;
-constexpr int kOffA1 = kOffGB1 + 2 * kGB1PlaneBytes;           // x~ rows, K-major
+constexpr int kOffA1 = kOffGB + 2 * kGroupPlaneBytes;          // x~ rows, K-major
 constexpr int kB1PlaneBytes = kHid * kK1Max * 4;
 constexpr int kOffB1 = kOffA1 + kA1Bytes;                      // layer-1 B planes
-constexpr int kOffBB = kOffB1 + 2 * kB1PlaneBytes;             // [b2_hi, b2_lo, 0...] rows, K = 8
-constexpr int kOffAC = kOffBB + kHid * 8 * 4;                  // constant A = [1, 1, 0...], K = 8
-constexpr int kOffSmall = kOffAC + kT * 8 * 4;
+constexpr int kOffSmall = kOffB1 + 2 * kB1PlaneBytes;
 constexpr int kSmW3 = 0, kSmB3 = 512, kSmStd = 520, kSmAvg = 528, kSmSd = 544, kSmGW3 = 560, kSmGB3 = 1072, kSmGStd = 1080,
-              kSmallFloats = 1088;
+              kSmB2 = 1088, kSmGB2 = 1152, kSmallFloats = 1216;
 constexpr int kOffBar = kOffSmall + kSmallFloats * 4;
 constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kSmemBytes <= 226 * 1024, "shared memory budget");
+static_assert(kOffGA % 1024 == 0 && kOffGB % 1024 == 0 && kOffWB % 1024 == 0, "MN-major images: swizzle-atom alignment");
 
 // ---- tensor memory columns
-constexpr uint32_t cZ1 = 0, cPhi = 64, cPlo = 128, cZ2 = 192, cG2 = 256, cG1 = 328;
+constexpr uint32_t cZ1 = 0, cPhi = 64, cPlo = 128, cZ2 = 192, cG2 = 256, cG1 = 320;
 
 // ---- peer-memory exchange (env-sharded update): system-scope release / acquire flags, relaxed system-scope data loads
 DEV void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -117,19 +115,15 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
     // ---- one-time setup
     if (warp == 0) tc05::tmem_alloc<512>(&tmem_slot);
     if (tid == 32) { tc05::mbar_init(bar, 1); tc05::mbar_fence_init(); }
-    for (int i = tid; i < kT * 8; i += kT)   // constant A of the bias UMMA
-        *reinterpret_cast<float*>(smem + kOffAC + tc05::operand_offset(i >> 3, i & 7, 8)) = (i & 7) < 2 ? 1.0f : 0.0f;
     for (int i = tid; i < kA1Bytes / 4; i += kT) reinterpret_cast<float*>(smem + kOffA1)[i] = 0.0f;
-    {   // columns 64..71 of [H1 | 1 | 0]: the ones column gives db2
-        const float one[8] = {1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        store_hi_lo_rows8(smem + kOffGB2, smem + kOffGB2 + kGB2PlaneBytes, tid, 64, one);
-    }
     tc05::fence_before_thread_sync();
     __syncthreads();
     tc05::fence_after_thread_sync();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
     const uint32_t w2_hi = tc05::smem_u32(smem + kOffW2), w2_lo = w2_hi + kWPlaneBytes;
+    const uint32_t wb_hi = tc05::smem_u32(smem + kOffWB), wb_lo = wb_hi + kWPlaneBytes;
+    const uint32_t ga_addr = tc05::smem_u32(smem + kOffGA), gb_addr = tc05::smem_u32(smem + kOffGB);
     uint32_t phase = 0;
     double acc_c = 0.0, acc_s = 0.0, acc_e = 0.0;   // thread 0: loss sums over the minibatches (persistent mode)
 
@@ -179,6 +173,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         float* const g = sharded ? A.px.data[A.px.rank] + px_off : g_local;
         // ------------------------------------------------------------ parameters -> operand images (Adam rewrote them)
         stage_w_planes(net.weight[1], smem + kOffW2, smem + kOffW2 + kWPlaneBytes, tid, kT);
+        stage_w_planes_backward(net.weight[1], smem + kOffWB, smem + kOffWB + kWPlaneBytes, tid, kT);
         for (int i = tid; i < kHid * K1; i += kT) {
             const int n = i / K1, k = i - n * K1;
             float full = 0.0f;
@@ -190,11 +185,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             *reinterpret_cast<float*>(smem + kOffB1 + off) = hi;                                   // [W_hi, b_hi, W_hi, 0]
             *reinterpret_cast<float*>(smem + kOffB1 + kB1PlaneBytes + off) = k <= S ? full - hi : 0.0f;   // [W_lo, b_lo, 0, 0]
         }
-        for (int i = tid; i < kHid * 8; i += kT) {
-            const int n = i >> 3, k = i & 7;
-            const float b2 = __ldcg(net.bias[1] + n), b2hi = tc05::tf32_hi(b2);
-            *reinterpret_cast<float*>(smem + kOffBB + tc05::operand_offset(n, k, 8)) = k == 0 ? b2hi : (k == 1 ? b2 - b2hi : 0.0f);
-        }
+        if (tid < kHid) { small[kSmB2 + tid] = __ldcg(net.bias[1] + tid); small[kSmGB2 + tid] = 0.0f; }
         for (int i = tid; i < OUT * kHid; i += kT) { small[kSmW3 + i] = __ldcg(net.weight[2] + i); small[kSmGW3 + i] = 0.0f; }
         if (tid < OUT) {
             small[kSmB3 + tid] = __ldcg(net.bias[2] + tid);
@@ -252,7 +243,8 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = (x[k] - small[kSmAvg + k]) / small[kSmSd + k];
         }
-        {   // x~ row (K-major A operand of layer 1) and the [X | 1 | 0] row (B operand of G1)
+        float xrow[16];   // [X | 1 | 0] row: the B operand of G1, written into the group buffer once G2 is done with it
+        {   // x~ row (K-major A operand of layer 1)
             float xr[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xr[k] = 0.0f;
@@ -268,14 +260,8 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S, K1)) = 1.0f;
 #pragma unroll
             for (int k = 0; k < 16; ++k) if (k == S) xr[k] = valid ? 1.0f : 0.0f;
-            if (N1 == 8) {
-                float x8[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) x8[k] = xr[k];
-                store_hi_lo_rows8(smem + kOffGB1, smem + kOffGB1 + kGB1PlaneBytes, tid, 0, x8);
-            } else {
-                store_hi_lo_rows(smem + kOffGB1, smem + kOffGB1 + kGB1PlaneBytes, tid, 0, xr);
-            }
+            for (int k = 0; k < 16; ++k) xrow[k] = xr[k];
         }
         tc05::fence_proxy_async_smem();
         tc05::fence_before_thread_sync();
@@ -296,7 +282,8 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
 
-        // ------------------------------------------------------------ H1 = GELU(Z1): TMEM planes (layer-2 A) + rows (G2's B)
+        // ------------------------------------------------------------ H1 = GELU(Z1): TMEM planes (layer-2 A); columns 0..31 also as
+        // rows of the group buffer (B operand of the first weight-gradient pass)
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             float z[16];
@@ -305,7 +292,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, z);
-            store_hi_lo_rows(smem + kOffGB2, smem + kOffGB2 + kGB2PlaneBytes, tid, 16 * c, z);
+            if (c < 2) store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 16 * c, z);
         }
         tc05::tmem_st_wait();
         tc05::fence_proxy_async_smem();
@@ -313,9 +300,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         __syncthreads();
         if (tid == 0) {
             tc05::fence_after_thread_sync();
-            tc05::mma_tf32(tmem_base + cZ2, tc05::make_smem_desc_ex(tc05::smem_u32(smem + kOffAC), 128, 256),
-                           tc05::make_smem_desc_ex(tc05::smem_u32(smem + kOffBB), 128, 256), tc05::make_idesc_tf32(kT, kHid), false);
-            issue_linear_ts(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, w2_hi, w2_lo, false, true);
+            issue_linear_ts(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, w2_hi, w2_lo, false);
             tc05::mma_commit(bar);
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
@@ -331,7 +316,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
             tc05::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j] + small[kSmB2 + 16 * c + j]);
 #pragma unroll
             for (int a = 0; a < kMaxOut; ++a) {
                 if (a < OUT) {
@@ -454,7 +439,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float dg;
-                gelu_and_grad(z[j], gz[j], dg);
+                gelu_and_grad(z[j] + small[kSmB2 + 16 * c + j], gz[j], dg);
                 float dh = 0.0f;
 #pragma unroll
                 for (int a = 0; a < kMaxOut; ++a) if (a < OUT) dh = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j], dh);
@@ -462,6 +447,13 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, dz);
             store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dz);
+            {   // db2 = column sums of dZ2
+                float w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = dz[j];
+                const float tot = warp_reduce16(w, lane);
+                if (!(lane & 1)) atomicAdd(&small[kSmGB2 + 16 * c + ((lane >> 1) & 15)], tot);
+            }
 #pragma unroll
             for (int a = 0; a < kMaxOut; ++a) {
                 if (a < OUT) {
@@ -479,9 +471,28 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         __syncthreads();
         if (tid == 0) {
             tc05::fence_after_thread_sync();
-            issue_linear_ts(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, w2_hi, w2_lo, true, false);   // dH1 over Z2
-            issue_weight_grad(tmem_base + cG2, tc05::smem_u32(smem + kOffGA), kGAPlaneBytes, tc05::smem_u32(smem + kOffGB2),
-                              kGB2PlaneBytes, 72);
+            issue_linear_ts_backward(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, wb_hi, wb_lo);   // dH1 over Z2
+            issue_weight_grad(tmem_base + cG2, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, 32);       // dW2[:, 0:32]
+            tc05::mma_commit(bar);
+        }
+        tc05::mbar_wait(bar, phase & 1); ++phase;
+        tc05::fence_after_thread_sync();
+        // second pass: H1[:, 32:64] (recomputed from Z1, still in tensor memory) into the same group buffer -> dW2[:, 32:64]
+#pragma unroll 1
+        for (int c = 2; c < 4; ++c) {
+            float z[16];
+            tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
+            tc05::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+            store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 16 * (c - 2), z);
+        }
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc05::fence_after_thread_sync();
+            issue_weight_grad(tmem_base + cG2 + 32, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, 32);
             tc05::mma_commit(bar);
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
@@ -502,13 +513,20 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
             store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dh);
         }
+        if (N1 == 8) {
+            float x8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x8[k] = xrow[k];
+            store_hi_lo_rows8(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, x8);
+        } else {
+            store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, xrow);
+        }
         tc05::fence_proxy_async_smem();
         tc05::fence_before_thread_sync();
         __syncthreads();
         if (tid == 0) {
             tc05::fence_after_thread_sync();
-            issue_weight_grad(tmem_base + cG1, tc05::smem_u32(smem + kOffGA), kGAPlaneBytes, tc05::smem_u32(smem + kOffGB1),
-                              kGB1PlaneBytes, N1);
+            issue_weight_grad(tmem_base + cG1, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, N1);
             tc05::mma_commit(bar);
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
@@ -520,22 +538,18 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             const int j = 16 * warp + (lane & 15);
             const bool row_owner = lane < 16;
 #pragma unroll 1
-            for (int c = 0; c < 9; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 float v[8];
                 tc05::tmem_ld_32x32b_x8(tl + cG2 + 8 * c, v);
                 tc05::tmem_ld_wait();
                 if (row_owner) {
-                    if (c < 8) {
-                        float* dst = g + oW1 + j * kHid + 8 * c;
-                        if (atomic) {
+                    float* dst = g + oW1 + j * kHid + 8 * c;
+                    if (atomic) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) dst[i] = v[i];
-                        }
+                        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
                     } else {
-                        if (atomic) atomicAdd(g + oB1 + j, v[0]); else g[oB1 + j] = v[0];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[i] = v[i];
                     }
                 }
             }
@@ -556,6 +570,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         }
         __syncthreads();   // the shared-memory accumulators of the head are complete
         for (int i = tid; i < OUT * kHid; i += kT) { if (atomic) atomicAdd(g + oW2 + i, small[kSmGW3 + i]); else g[oW2 + i] = small[kSmGW3 + i]; }
+        if (tid < kHid) { if (atomic) atomicAdd(g + oB1 + tid, small[kSmGB2 + tid]); else g[oB1 + tid] = small[kSmGB2 + tid]; }
         if (tid < OUT) {
             if (atomic) atomicAdd(g + oB2 + tid, small[kSmGB3 + tid]); else g[oB2 + tid] = small[kSmGB3 + tid];
             if (gaussian) { if (atomic) atomicAdd(g + oStd + tid, small[kSmGStd + tid]); else g[oStd + tid] = small[kSmGStd + tid]; }

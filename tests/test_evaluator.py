@@ -50,12 +50,12 @@ def _reference_function():
 def _actor(device):
     from elegantrl_b200.agents.nets import ActorPPO
     th.manual_seed(5)
-    actor = ActorPPO([64, 64], 3, 1).to(device)
+    actor = ActorPPO([64, 64], 3, 1)          # built on the CPU (one RNG stream), then moved: identical weights on every device
     with th.no_grad():
         for layer in actor.net:
             if hasattr(layer, "bias"):
                 layer.bias += 0.1 * th.randn_like(layer.bias)
-    return actor
+    return actor.to(device)
 
 
 def test_generic_path_equals_reference_function_on_cpu():
