@@ -644,7 +644,7 @@ int b200rl_replay_append(const b200rl_replay_buffer* buffer, int32_t p, int32_t 
     B200RL_REQUIRE(buffer && buffer->states && buffer->actions && buffer->rewards && buffer->undones && buffer->unmasks,
                    "replay_append: NULL buffer");
     B200RL_REQUIRE(states && actions && rewards && undones && unmasks, "replay_append: NULL rollout tensor");
-    B200RL_REQUIRE(rows >= 1 && rows <= buffer->max_size && p >= 0 && p < buffer->max_size, "replay_append: p=%d rows=%d max_size=%d", p,
+    B200RL_REQUIRE(rows >= 1 && rows <= buffer->max_size && p >= 0 && p <= buffer->max_size, "replay_append: p=%d rows=%d max_size=%d", p,
                    rows, buffer->max_size);
     const int64_t total = (int64_t)rows * buffer->num_seqs * (buffer->state_dim + buffer->action_dim + 3);
     const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);

@@ -13,10 +13,13 @@
 //     dW = dZ^T X (a contraction over the SAMPLE axis) reach the tensor core without a transposition through shared memory.
 //     MN-major kind::tf32 operands exist in ONE layout only, SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major
 //     tf32 operands, SW128_32B is the only available smem layout"; measured: with any other layout type the UMMA writes
-//     nothing, profiles/r02_v4_mn_major_probe.log).  Atom = 32 columns (128 B) x 4 samples at 128 B, Swizzle<2,5,2> in bits:
-//       offset(b, c) = (c/32)*LBO + (b/4)*512 + (b%4)*128 + (c%32)*4,   byte bits [2,4) ^= byte bits [4,6)
-//     i.e. inside every 16-byte unit u the four elements are permuted by e -> e ^ (u & 3): a compile-time shuffle of the
-//     registers a thread stores.  LBO (between 32-column groups) = 128 samples / 4 * 512 = 16 KB.
+//     nothing, profiles/r02_v4_mn_major_probe.log).  The layout was decoded on the B200 by filling the operand region with
+//     its own word index against a one-hot second operand (tools/tc_mn_probe3.cu, profiles/r02_v4_mn_major_decode.log):
+//     atom = 32 columns (128 B) x 4 samples at 128 B, and the 32-BYTE chunk index of a row is XORed with the row index:
+//       offset(b, c) = (c/32)*LBO + (b/4)*SBO + (b%4)*128 + (((c%32)*4) ^ ((b%4) << 5))
+//     (Swizzle<2,5,2> on byte addresses: bits [5,7) ^= bits [7,9)); descriptor LBO = stride between 32-column groups, SBO =
+//     stride between 4-sample groups, for A and for B.  A sample's 16-byte stores simply go to unit u ^ (2 * (b % 4)); the
+//     four rows of an atom thereby hit four different bank groups.  LBO = 128 samples / 4 * 512 = 16 KB.
 //   * the backward image of W2 (for dH1 = dZ2 W2: B [n = input][K = output]) is the same layout with MN = input feature,
 //     K = output feature: offset(j, k) = (k/32)*8192 + (j/4)*512 + (j%4)*128 + (k%32)*4, swizzled.
 #pragma once
@@ -86,7 +89,7 @@ DEV void stage_w_planes(const float* W, unsigned char* hi, unsigned char* lo, in
         *reinterpret_cast<float*>(lo + off) = w - h;
     }
 }
-DEV uint32_t mn_swizzle(uint32_t byte_off) { return byte_off ^ (((byte_off >> 4) & 3u) << 2); }
+DEV uint32_t mn_swizzle(uint32_t byte_off) { return byte_off ^ (((byte_off >> 7) & 3u) << 5); }
 // ... and its backward image (MN = input feature k, K = output feature j), hi / lo planes
 DEV void stage_w_planes_backward(const float* W, unsigned char* hi, unsigned char* lo, int tid, int nthreads) {
     for (int i = tid; i < kHid * kHid; i += nthreads) {
@@ -112,30 +115,19 @@ DEV void store_hi_lo_tmem(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)
 DEV void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// NV consecutive columns [col0, col0 + NV) of sample b's row -> hi / lo row-written images (col0 % 16 == 0 or NV == 8 with
-// col0 % 8 == 0; the NV columns stay inside one 32-column group).  Unit u = 16-byte unit inside the 128-byte row; its four
-// elements are stored permuted by e -> e ^ (u & 3) (the layout's swizzle), a compile-time choice of registers.
+// NV consecutive columns [col0, col0 + NV) of sample b's row -> hi / lo row-written images (col0 % 4 == 0; the NV columns stay
+// inside one 32-column group).  16-byte unit u of the row is stored at unit u ^ (2 * (b % 4)) (the layout's 32-byte swizzle).
 template <int NV>
 DEV void store_hi_lo_rows_n(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[NV]) {
     const uint32_t row = (uint32_t)(col0 >> 5) * kRowLBO + (uint32_t)(b >> 2) * kMnSBO + (uint32_t)(b & 3) * 128;
-    const uint32_t u0 = (uint32_t)(col0 & 31) >> 2;   // NV / 4 consecutive units; u0 % (NV / 4) == 0, so (u0 + q) & 3 == q & 3 ... for NV = 16; NV = 8: (u0 & 2) | q
-    const uint32_t hi0 = tc05::smem_u32(hi_plane) + row + u0 * 16, lo0 = tc05::smem_u32(lo_plane) + row + u0 * 16;
+    const uint32_t u0 = (uint32_t)(col0 & 31) >> 2, x = (uint32_t)(b & 3) << 1;
+    const uint32_t hi0 = tc05::smem_u32(hi_plane) + row, lo0 = tc05::smem_u32(lo_plane) + row;
 #pragma unroll
     for (int q = 0; q < NV / 4; ++q) {
-        float h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { h[e] = tc05::tf32_hi(v[4 * q + e]); l[e] = v[4 * q + e] - h[e]; }
-        // position p of the unit holds element p ^ s, s = (u0 + q) & 3: s is only known at run time through u0's bit 1 when
-        // NV == 8 (u0 in {0, 2, 4, 6}); resolve it with one uniform branch on (u0 & 2)
-        const int s_lo = q & 3;
-        if (NV == 16 || !(u0 & 2)) {
-            st_shared_v4(hi0 + q * 16, h[0 ^ s_lo], h[1 ^ s_lo], h[2 ^ s_lo], h[3 ^ s_lo]);
-            st_shared_v4(lo0 + q * 16, l[0 ^ s_lo], l[1 ^ s_lo], l[2 ^ s_lo], l[3 ^ s_lo]);
-        } else {
-            const int s2 = s_lo ^ 2;
-            st_shared_v4(hi0 + q * 16, h[0 ^ s2], h[1 ^ s2], h[2 ^ s2], h[3 ^ s2]);
-            st_shared_v4(lo0 + q * 16, l[0 ^ s2], l[1 ^ s2], l[2 ^ s2], l[3 ^ s2]);
-        }
+        const uint32_t unit = ((u0 + q) ^ x) * 16;
+        const float h0 = tc05::tf32_hi(v[4 * q]), h1 = tc05::tf32_hi(v[4 * q + 1]), h2 = tc05::tf32_hi(v[4 * q + 2]), h3 = tc05::tf32_hi(v[4 * q + 3]);
+        st_shared_v4(hi0 + unit, h0, h1, h2, h3);
+        st_shared_v4(lo0 + unit, v[4 * q] - h0, v[4 * q + 1] - h1, v[4 * q + 2] - h2, v[4 * q + 3] - h3);
     }
 }
 DEV void store_hi_lo_rows(unsigned char* hi_plane, unsigned char* lo_plane, int b, int col0, const float (&v)[16]) {

@@ -1,6 +1,6 @@
 // Second probe: MN-major tf32 operands need the SWIZZLE_128B_BASE32B layout type ("for mn-major tf32 operands, SW128_32B is
 // the only available smem layout", cutlass sm100_common.inl).  Atom (cute Layout_MN_SW128_32B_Atom): 32 MN elements (128 B)
-// contiguous x 4 K rows at 128 B, Swizzle<2,5,2> in bits = byte address bits [2,4) ^= bits [4,6).
+// contiguous x 4 K rows at 128 B, Swizzle<2,5,2> on BYTE addresses: bits [5,7) ^= bits [7,9) (decoded by tc_mn_probe3.cu).
 //   element (mn, k) -> (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + (mn % 32) * 4, then swizzled
 // Tries the writer with / without the swizzle and both assignments of the descriptor's LBO / SBO fields.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -o tools/bin/tc_mn_probe2 tools/tc_mn_probe2.cu
@@ -24,7 +24,7 @@ __device__ __forceinline__ uint64_t desc_sw32b(uint32_t addr, uint32_t lbo, uint
 }
 __device__ __forceinline__ uint32_t sw_addr(uint32_t mn, uint32_t k, uint32_t lbo, int swz) {
     uint32_t a = (mn / 32) * lbo + (k / 4) * kSBO + (k % 4) * 128 + (mn % 32) * 4;
-    if (swz) a ^= ((a >> 4) & 3) << 2;
+    if (swz) a ^= ((a >> 7) & 3) << 5;   // decoded by tools/tc_mn_probe3.cu: 32-byte chunk index ^= row index
     return a;
 }
 
