@@ -8,7 +8,8 @@
 // One minibatch = four launches over tiles of 32 sampled transitions (generic depth / widths, FP32 pipe, the tile routines of
 // mlp_tile.cuh / mlp_grad.cuh; parameters are read L2-coherently because the last CTA of a launch rewrites them):
 //   label   s' -> actor (rsample eps_next) -> target ensemble -> q_label = r + undone * gamma * (min_e Q - logp' * alpha)
-//   critic  (s, a) -> ensemble forward / backward, one decoder at a time (its caches fit in shared memory) -> gradients;
+//   critic  (s, a) -> ensemble forward / backward, one decoder per CTA (grid = tiles x E: the decoders are independent given
+//           the shared encoder output, and the encoder's gradient is linear in their contributions) -> gradients;
 //           last CTA: clip_grad_norm_ + Adam over the critic's parameter list, then the soft update of the target
 //   pgrad   s -> actor (rsample eps_pg) -> target ensemble forward and DATA gradient -> d obj / d tanh(action), sums of
 //           logp and Q; last CTA: temperature step (alpha taken after it, before the clamp), obj_actor
@@ -202,7 +203,7 @@ DEV void apply_group(const b200rl_param_group& grp, const AdamScalars& as, const
 DEV bool last_block(unsigned int* ticket, int* s_flag) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) *s_flag = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
     __syncthreads();
     if (*s_flag) __threadfence();
     return *s_flag != 0;
@@ -248,6 +249,8 @@ __global__ void __launch_bounds__(kNT) sac_label_kernel(const __grid_constant__ 
         if (threadIdx.x < TB) s_minq[threadIdx.x] = fminf(s_minq[threadIdx.x], q[T::elem(0, threadIdx.x)]);
         __syncthreads();
     }
+    for (int idx = threadIdx.x; idx < TB * Ad; idx += kNT)
+        if (slot0 + idx / Ad < A.batch) A.d_tanh[(size_t)slot0 * Ad + idx] = 0.0f;
     if (threadIdx.x < TB && s_row[threadIdx.x] >= 0) {
         const int b = threadIdx.x;
         const int64_t r = s_row[b];
@@ -276,7 +279,8 @@ DEV void ensemble_pass(const SacArgs& A, const b200rl_sac_critic& cri, float* sm
     const float inv_be = 1.0f / ((float)A.batch * (float)E);
     float q_sum = 0.0f, td = 0.0f;   // valid in threads < TB
     const int enc_numel = mlp_numel(cri.encoder), dec_numel = mlp_numel(cri.decoder[0]);
-    for (int e = 0; e < E; ++e) {
+    {
+        const int e = blockIdx.y;   // one decoder per CTA
         const float* xs[B200RL_MAX_LINEAR + 1];
         const float* gs[B200RL_MAX_LINEAR + 1];
         mlp_forward_cached(cri.decoder[e], false, enc, cache, out, xs, gs);
@@ -306,9 +310,9 @@ DEV void ensemble_pass(const SacArgs& A, const b200rl_sac_critic& cri, float* sm
         // d / d (state, action) through the raw encoder; only the action rows are needed
         data_grad<TB, kNT, WM>(cri.encoder.weight[0], d_enc, nullptr, dzA, d0, S + Ad);
         __syncthreads();
-        for (int idx = threadIdx.x; idx < TB * Ad; idx += kNT) {
+        for (int idx = threadIdx.x; idx < TB * Ad; idx += kNT) {   // the E decoders' CTAs add up (zeroed by the label kernel)
             const int b = idx / Ad, a = idx - b * Ad;
-            if (s_row[b] >= 0) A.d_tanh[(size_t)(slot0 + b) * Ad + a] = dzA[T::elem(S + a, b)];
+            if (s_row[b] >= 0) atomicAdd(&A.d_tanh[(size_t)(slot0 + b) * Ad + a], dzA[T::elem(S + a, b)]);
         }
     }
     q_mean_out = q_sum;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(kNT) sac_pgrad_kernel(const __grid_constant__ 
     if (threadIdx.x < TB) {
         const int b = threadIdx.x;
         logp = actor_head(out, Ad, b, A.eps_pg, A.seed, A.draw, (uint32_t)(slot0 + b), kStreamSacPg, sa, S);
-        if (s_row[b] >= 0) A.logp[slot0 + b] = logp; else logp = 0.0f;
+        if (s_row[b] >= 0 && blockIdx.y == 0) A.logp[slot0 + b] = logp; else logp = 0.0f;   // counted once over the decoders' CTAs
     }
     __syncthreads();
     float q_mean, td_unused;
@@ -747,8 +751,8 @@ int b200rl_sac_update(const b200rl_sac_actor* actor, const b200rl_sac_critic* cr
         A.adam_alpha = group_scalars(alpha_group, alpha_group->step + u + 1);
         A.last_update = u == update_times - 1;
         sac_label_kernel<<<tiles, kNT, L.smem_label, stream>>>(A);
-        sac_critic_kernel<<<tiles, kNT, L.smem_ensemble, stream>>>(A);
-        sac_pgrad_kernel<<<tiles, kNT, L.smem_ensemble, stream>>>(A);
+        sac_critic_kernel<<<dim3(tiles, (unsigned)critic->num_ensembles), kNT, L.smem_ensemble, stream>>>(A);
+        sac_pgrad_kernel<<<dim3(tiles, (unsigned)critic->num_ensembles), kNT, L.smem_ensemble, stream>>>(A);
         sac_actor_kernel<<<tiles, kNT, L.smem_actor, stream>>>(A);
     }
     B200RL_COUNT_LAUNCH(4 * update_times);

@@ -38,6 +38,7 @@ struct UpdateArgs {
     const double* stat_sums;   // this shard's advantage sums (b200rl_gae)
     double count_all, count_lat;
     float* stats_out;          // [4] reduced statistics
+    int profile;               // B200RL_PROFILE=1: clock64 phase marks of the actor CTA into the workspace header (+64 B)
 };
 
 // update_tc.cu: the tcgen05 implementation for S -> 64 -> 64 -> OUT GELU nets
@@ -64,9 +65,37 @@ DEV void adam_one(float& p, float& m, float& v, float g, float b1, float b2, flo
     p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-as.step_size, m), denom));         // addcdiv_(exp_avg, denom, -step_size)
 }
 
+// The same update with MUFU reciprocal / reciprocal-square-root instead of the IEEE division and square root (which expand to
+// ~190 instructions per element and were half of the tcgen05 update kernel's instruction stream, executed by only four warps):
+// sqrt(v) = v * rsqrt(v), / bc2_sqrt -> * (1 / bc2_sqrt), the final quotient with one Newton step on the approximate
+// reciprocal.  Deviates from torch by <= 2 ulp per step (rtol 1e-4 parity is unaffected; replicas on several GPUs still agree
+// bit for bit because they all run this arithmetic).
+DEV void adam_one_fast(float& p, float& m, float& v, float g, float b1, float b2, float eps, const AdamScalars& as, float inv_bc2_sqrt) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - b1));
+    v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(1.0f - b2, g), g));
+    float rs, r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(v, 1e-37f)));   // one MUFU each (the _rn intrinsics expand to ~50 instructions)
+    const float sq = v * rs;
+    const float denom = fmaf(sq, inv_bc2_sqrt, eps);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(denom));
+    r = fmaf(fmaf(-denom, r, 1.0f), r, r);                                   // one Newton step: relative error ~1e-7
+    p = fmaf(-as.step_size * m, r, p);
+}
+template <bool FAST>
+DEV void adam_step(float& p, float& m, float& v, float g, float b1, float b2, float eps, const AdamScalars& as, float inv_bc2_sqrt) {
+    if (FAST) adam_one_fast(p, m, v, g, b1, b2, eps, as, inv_bc2_sqrt);
+    else adam_one(p, m, v, g, b1, b2, eps, as);
+}
+
 // clip_grad_norm_ + Adam.step for one net.  The whole CTA computes the norm of the net's gradient; it then updates
 // the part `part` of `nparts` of every tensor (nparts = 1: the whole net; > 1: the CTAs of a cluster share the net).
-template <int NT>
+// GSMEM: the gradient lives in shared memory (plain loads) instead of the L2-resident workspace (ld.global.cg)
+template <bool GSMEM>
+DEV float ld_grad(const float* p) { return GSMEM ? *p : __ldcg(p); }
+template <bool GSMEM>
+DEV float4 ld_grad4(const float4* p) { return GSMEM ? *p : __ldcg(p); }
+
+template <int NT, bool GSMEM = false, bool FAST = false>
 DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
                    float clip_grad_norm, float* red, int part = 0, int nparts = 1) {
     // squared norm of the whole gradient: batches of 8 independent L2 loads per thread (a plain loop would wait for
@@ -75,14 +104,14 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
     for (int i0 = threadIdx.x; i0 < numel; i0 += 8 * NT) {
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (i0 + q * NT < numel) ? __ldcg(g + i0 + q * NT) : 0.0f;
+        for (int q = 0; q < 8; ++q) v[q] = (i0 + q * NT < numel) ? ld_grad<GSMEM>(g + i0 + q * NT) : 0.0f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) ss = fmaf(v[q], v[q], ss);
     }
     float total_norm = sqrtf(block_sum<NT>(ss, red));
     float coef = 1.0f;
     if (clip_grad_norm > 0.0f) coef = fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f);
-    const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps;
+    const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps, inv_bc2 = 1.0f / as.bc2_sqrt;
     const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
     const int first = part * NT + threadIdx.x, stride = nparts * NT;
     // Every tensor is visited in rounds of up to kBatch tensors: all loads of a round are issued before any
@@ -119,7 +148,7 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
         for (int q = 0; q < kBatch; ++q) {
             have[q] = vecs[q] && first < (cnt[q] >> 2);
             if (have[q]) {
-                gg[q] = __ldcg(reinterpret_cast<const float4*>(g + goff[q]) + first);
+                gg[q] = ld_grad4<GSMEM>(reinterpret_cast<const float4*>(g + goff[q]) + first);
                 pp[q] = __ldcg(reinterpret_cast<const float4*>(P[q]) + first);
                 mm[q] = __ldcg(reinterpret_cast<const float4*>(M[q]) + first);
                 vv[q] = __ldcg(reinterpret_cast<const float4*>(V[q]) + first);
@@ -128,10 +157,10 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
 #pragma unroll
         for (int q = 0; q < kBatch; ++q) {
             if (have[q]) {
-                adam_one(pp[q].x, mm[q].x, vv[q].x, gg[q].x * coef, b1, b2, eps, as);
-                adam_one(pp[q].y, mm[q].y, vv[q].y, gg[q].y * coef, b1, b2, eps, as);
-                adam_one(pp[q].z, mm[q].z, vv[q].z, gg[q].z * coef, b1, b2, eps, as);
-                adam_one(pp[q].w, mm[q].w, vv[q].w, gg[q].w * coef, b1, b2, eps, as);
+                adam_step<FAST>(pp[q].x, mm[q].x, vv[q].x, gg[q].x * coef, b1, b2, eps, as, inv_bc2);
+                adam_step<FAST>(pp[q].y, mm[q].y, vv[q].y, gg[q].y * coef, b1, b2, eps, as, inv_bc2);
+                adam_step<FAST>(pp[q].z, mm[q].z, vv[q].z, gg[q].z * coef, b1, b2, eps, as, inv_bc2);
+                adam_step<FAST>(pp[q].w, mm[q].w, vv[q].w, gg[q].w * coef, b1, b2, eps, as, inv_bc2);
                 reinterpret_cast<float4*>(P[q])[first] = pp[q];
                 reinterpret_cast<float4*>(M[q])[first] = mm[q];
                 reinterpret_cast<float4*>(V[q])[first] = vv[q];
@@ -143,18 +172,31 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
             if (vecs[q]) {
                 const float4* g4 = reinterpret_cast<const float4*>(g + goff[q]);
                 float4 *p4 = reinterpret_cast<float4*>(P[q]), *m4 = reinterpret_cast<float4*>(M[q]), *v4 = reinterpret_cast<float4*>(V[q]);
-                for (int i = first + stride; i < (cnt[q] >> 2); i += stride) {
-                    float4 a = __ldcg(g4 + i), b = __ldcg(p4 + i), c = __ldcg(m4 + i), d = __ldcg(v4 + i);
-                    adam_one(b.x, c.x, d.x, a.x * coef, b1, b2, eps, as);
-                    adam_one(b.y, c.y, d.y, a.y * coef, b1, b2, eps, as);
-                    adam_one(b.z, c.z, d.z, a.z * coef, b1, b2, eps, as);
-                    adam_one(b.w, c.w, d.w, a.w * coef, b1, b2, eps, as);
-                    p4[i] = b; m4[i] = c; v4[i] = d;
+                // up to 4 items per trip, all their loads issued before any arithmetic (one L2 latency per trip, not per item)
+                const int n4 = cnt[q] >> 2;
+                for (int i = first + stride; i < n4; i += 4 * stride) {
+                    float4 a[4], b[4], c[4], d[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = i + u * stride;
+                        if (idx < n4) { a[u] = ld_grad4<GSMEM>(g4 + idx); b[u] = __ldcg(p4 + idx); c[u] = __ldcg(m4 + idx); d[u] = __ldcg(v4 + idx); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = i + u * stride;
+                        if (idx < n4) {
+                            adam_step<FAST>(b[u].x, c[u].x, d[u].x, a[u].x * coef, b1, b2, eps, as, inv_bc2);
+                            adam_step<FAST>(b[u].y, c[u].y, d[u].y, a[u].y * coef, b1, b2, eps, as, inv_bc2);
+                            adam_step<FAST>(b[u].z, c[u].z, d[u].z, a[u].z * coef, b1, b2, eps, as, inv_bc2);
+                            adam_step<FAST>(b[u].w, c[u].w, d[u].w, a[u].w * coef, b1, b2, eps, as, inv_bc2);
+                            p4[idx] = b[u]; m4[idx] = c[u]; v4[idx] = d[u];
+                        }
+                    }
                 }
             } else {
                 for (int i = first; i < cnt[q]; i += stride) {
                     float pi = __ldcg(P[q] + i), mi = __ldcg(M[q] + i), vi = __ldcg(V[q] + i);
-                    adam_one(pi, mi, vi, __ldcg(g + goff[q] + i) * coef, b1, b2, eps, as);
+                    adam_step<FAST>(pi, mi, vi, ld_grad<GSMEM>(g + goff[q] + i) * coef, b1, b2, eps, as, inv_bc2);
                     P[q][i] = pi; M[q][i] = mi; V[q][i] = vi;
                 }
             }

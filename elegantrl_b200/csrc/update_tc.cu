@@ -38,7 +38,7 @@ constexpr int kB1PlaneBytes = kHid * kK1Max * 4;
 constexpr int kOffB1 = kOffA1 + kA1Bytes;                      // layer-1 B planes
 constexpr int kOffSmall = kOffB1 + 2 * kB1PlaneBytes;
 constexpr int kSmW3 = 0, kSmB3 = 512, kSmStd = 520, kSmAvg = 528, kSmSd = 544, kSmGW3 = 560, kSmGB3 = 1072, kSmGStd = 1080,
-              kSmB2 = 1088, kSmGB2 = 1152, kSmallFloats = 1216;
+              kSmB2 = 1088, kSmGB2 = 1152, kSmW0 = 1216, kSmB0 = 1216 + 64 * kMaxS, kSmallFloats = kSmB0 + 64;
 constexpr int kOffBar = kOffSmall + kSmallFloats * 4;
 constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kSmemBytes <= 226 * 1024, "shared memory budget");
@@ -89,6 +89,85 @@ DEV void px_round(const b200rl_peer_exchange& px, int chan, uint32_t value, Work
     __syncthreads();
 }
 
+// Parameters of one net -> operand images and the small shared-memory tables.  Every load is issued before anything is stored
+// (ONE L2 latency per minibatch, not one per element).  Not inlined: its 43 staging registers would otherwise be live across
+// the minibatch loop's already full register file.
+__device__ __noinline__ void stage_params(const b200rl_net& net, float* small, uint32_t w2_hi, uint32_t w2_lo, uint32_t wb_hi,
+                                          uint32_t wb_lo, int tid, int S, int OUT, bool gaussian) {
+    {
+            float4 w[8];   // W2: 4096 floats = 8 float4 per thread
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q] = __ldcg(reinterpret_cast<const float4*>(net.weight[1]) + tid + kT * q);
+            // the small tensors as one index space: W0 [64 x S] | b0 | b1 | W3 [OUT x 64] | b3 | action_std_log
+            const int nW0 = kHid * S, nW3 = OUT * kHid;
+            const int total = nW0 + 2 * kHid + nW3 + OUT + (gaussian ? OUT : 0);
+            float sv[11];
+#pragma unroll
+            for (int q = 0; q < 11; ++q) {
+                int idx = tid + kT * q;
+                const float* ptr = nullptr;
+                if (idx < total) {
+                    if (idx < nW0) ptr = net.weight[0] + idx;
+                    else if ((idx -= nW0) < kHid) ptr = net.bias[0] + idx;
+                    else if ((idx -= kHid) < kHid) ptr = net.bias[1] + idx;
+                    else if ((idx -= kHid) < nW3) ptr = net.weight[2] + idx;
+                    else if ((idx -= nW3) < OUT) ptr = net.bias[2] + idx;
+                    else ptr = net.action_std_log + (idx - OUT);
+                }
+                sv[q] = ptr ? __ldcg(ptr) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {   // forward (K-major) and backward (MN-major) images of W2, hi / lo planes
+                const int i = 4 * (tid + kT * q), n = i >> 6, k = i & 63;
+                const float v4[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { h[e] = tc05::tf32_hi(v4[e]); l[e] = v4[e] - h[e]; }
+                const uint32_t offf = tc05::operand_offset(n, k, kHid);   // 4 consecutive k: one 16-byte chunk
+                st_shared_v4(w2_hi + offf, h[0], h[1], h[2], h[3]);
+                st_shared_v4(w2_lo + offf, l[0], l[1], l[2], l[3]);
+                // backward image: MN = k (contiguous), K = n: 4 consecutive k = one 16-byte unit of row n
+                const uint32_t offb = mn_swizzle((uint32_t)(k >> 5) * kWbLBO + (uint32_t)(n >> 2) * kMnSBO + (uint32_t)(n & 3) * 128 + (uint32_t)(k & 31) * 4);
+                st_shared_v4(wb_hi + offb, h[0], h[1], h[2], h[3]);
+                st_shared_v4(wb_lo + offb, l[0], l[1], l[2], l[3]);
+            }
+#pragma unroll
+            for (int q = 0; q < 11; ++q) {
+                int idx = tid + kT * q;
+                if (idx < total) {
+                    if (idx < nW0) small[kSmW0 + idx] = sv[q];
+                    else if ((idx -= nW0) < kHid) small[kSmB0 + idx] = sv[q];
+                    else if ((idx -= kHid) < kHid) { small[kSmB2 + idx] = sv[q]; small[kSmGB2 + idx] = 0.0f; }
+                    else if ((idx -= kHid) < nW3) { small[kSmW3 + idx] = sv[q]; small[kSmGW3 + idx] = 0.0f; }
+                    else if ((idx -= nW3) < OUT) { small[kSmB3 + idx] = sv[q]; small[kSmGB3 + idx] = 0.0f; }
+                    else small[kSmStd + (idx - OUT)] = sv[q];
+                }
+            }
+            if (tid < OUT) small[kSmGStd + tid] = 0.0f;
+            if (tid < S) {
+                small[kSmAvg + tid] = net.state_avg ? net.state_avg[tid] : 0.0f;
+                small[kSmSd + tid] = net.state_std ? net.state_std[tid] + 1e-4f : 1.0f;
+            }
+        }
+}
+
+// clip + Adam of one net, out of line for the same reason (its batched loads use 64 + registers of their own)
+__device__ __noinline__ void apply_from_smem(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
+                                             float clip_grad_norm, float* red) {
+    apply_net<kT, true, true>(net, opt, as, g, numel, clip_grad_norm, red);
+}
+__device__ __noinline__ void apply_from_global(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
+                                               float clip_grad_norm, float* red) {
+    apply_net<kT, false, true>(net, opt, as, g, numel, clip_grad_norm, red);
+}
+
+#define TC_MARK(i) do { if (A.profile && ni == 0 && tid == 0 && u == U - 1) reinterpret_cast<long long*>(A.hdr)[8 + (i)] = clock64(); } while (0)
+
+// OUTC / SC: compile-time capacities (>= the nets' OUT / S) of the per-thread head / state arrays.  The body is straight-line
+// code executed once per minibatch by four warps: with the capacities at their maxima (8, 11) it was 15 k instructions (240 KB)
+// and instruction fetch was the top stall (profiles/r02_v7_update_tc_phases_before_code_size_fix.log); sized to the net it fits
+// the instruction cache.
+template <int OUTC, int SC>
 __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_constant__ UpdateArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ float red[32];
@@ -169,34 +248,17 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
     for (int u = 0; u < U; ++u) {
         // env-sharded: this minibatch's gradient goes to the own exchange buffer (two alternate so that a rank that is one
         // minibatch ahead never overwrites what a peer still reads); the reduced gradient lands in the workspace as usual
-        const int px_off = px_off0 + (u & 1) * px_parity_stride;
-        float* const g = sharded ? A.px.data[A.px.rank] + px_off : g_local;
+        // (parity of the GLOBAL minibatch count, so that consecutive minibatches alternate across calls as well: writing buffer p
+        // at minibatch g needs the wait of g - 1 behind it, which every peer passes only after it has read g - 2 = the last use of p)
+        const int px_off = px_off0 + (int)((A.px.epoch + (uint32_t)u) & 1u) * px_parity_stride;
+        // persistent mode: the flat gradient of this minibatch lives in SHARED memory (the dZ row buffer is free once G1 is done);
+        // env-sharded: the own exchange buffer, the reduced sum then goes to shared memory; several tiles: the global workspace
+        float* const g_smem = reinterpret_cast<float*>(smem + kOffGA);
+        float* const g = sharded ? A.px.data[A.px.rank] + px_off : (persistent ? g_smem : g_local);
         // ------------------------------------------------------------ parameters -> operand images (Adam rewrote them)
-        stage_w_planes(net.weight[1], smem + kOffW2, smem + kOffW2 + kWPlaneBytes, tid, kT);
-        stage_w_planes_backward(net.weight[1], smem + kOffWB, smem + kOffWB + kWPlaneBytes, tid, kT);
-        for (int i = tid; i < kHid * K1; i += kT) {
-            const int n = i / K1, k = i - n * K1;
-            float full = 0.0f;
-            if (k < S) full = __ldcg(net.weight[0] + n * S + k);
-            else if (k == S) full = __ldcg(net.bias[0] + n);
-            else if (k <= 2 * S) full = __ldcg(net.weight[0] + n * S + (k - S - 1));
-            const float hi = tc05::tf32_hi(full);
-            const uint32_t off = tc05::operand_offset(n, k, K1);
-            *reinterpret_cast<float*>(smem + kOffB1 + off) = hi;                                   // [W_hi, b_hi, W_hi, 0]
-            *reinterpret_cast<float*>(smem + kOffB1 + kB1PlaneBytes + off) = k <= S ? full - hi : 0.0f;   // [W_lo, b_lo, 0, 0]
-        }
-        if (tid < kHid) { small[kSmB2 + tid] = __ldcg(net.bias[1] + tid); small[kSmGB2 + tid] = 0.0f; }
-        for (int i = tid; i < OUT * kHid; i += kT) { small[kSmW3 + i] = __ldcg(net.weight[2] + i); small[kSmGW3 + i] = 0.0f; }
-        if (tid < OUT) {
-            small[kSmB3 + tid] = __ldcg(net.bias[2] + tid);
-            small[kSmStd + tid] = gaussian ? __ldcg(net.action_std_log + tid) : 0.0f;
-            small[kSmGB3 + tid] = 0.0f;
-            small[kSmGStd + tid] = 0.0f;
-        }
-        if (tid < S) {
-            small[kSmAvg + tid] = net.state_avg ? net.state_avg[tid] : 0.0f;
-            small[kSmSd + tid] = net.state_std ? net.state_std[tid] + 1e-4f : 1.0f;
-        }
+        // every load of the minibatch's parameters is issued before anything is stored: ONE L2 latency, not one per element
+        TC_MARK(0);
+        stage_params(net, small, w2_hi, w2_lo, wb_hi, wb_lo, tid, S, OUT, gaussian);
 
         // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n)
         const int64_t* ids_u = A.ids ? A.ids + (persistent ? (size_t)u * A.local_batch : 0) : nullptr;
@@ -204,12 +266,12 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         const int slot = tile * kT + tid;
         const bool valid = slot < A.local_batch;
         float um = 0.f, lp_old = 0.f, adv = 0.f, rs = 0.f;
-        float act[kMaxOut];
-        float x[kMaxS];
+        float act[OUTC];
+        float x[SC];
 #pragma unroll
-        for (int a = 0; a < kMaxOut; ++a) act[a] = 0.0f;
+        for (int a = 0; a < OUTC; ++a) act[a] = 0.0f;
 #pragma unroll
-        for (int k = 0; k < kMaxS; ++k) x[k] = 0.0f;
+        for (int k = 0; k < SC; ++k) x[k] = 0.0f;
         if (valid) {
             const int Adim = discrete ? 1 : A.net[0].dims[3];
             if (packed) {
@@ -218,9 +280,9 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 const float4 tail = *reinterpret_cast<const float4*>(recp + rec_tail);
                 um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
 #pragma unroll
-                for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = recp[k];
+                for (int k = 0; k < SC; ++k) if (k < S) x[k] = recp[k];
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) if (a < Adim) act[a] = recp[rec_act + a];
+                for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = recp[rec_act + a];
             } else {
                 const int64_t id = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
                 const int64_t tn = (id % H) * N + id / H;
@@ -230,43 +292,47 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 if (normalise) adv = (adv - s_stats[0]) / (s_stats[1] + 1e-5f);
                 rs = A.buf.reward_sums[tn];
 #pragma unroll
-                for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = A.buf.states[tn * S + k];
+                for (int k = 0; k < SC; ++k) if (k < S) x[k] = A.buf.states[tn * S + k];
                 if (discrete) act[0] = (float)reinterpret_cast<const int32_t*>(A.buf.actions)[tn];
                 else {
 #pragma unroll
-                    for (int a = 0; a < kMaxOut; ++a) if (a < Adim) act[a] = A.buf.actions[tn * Adim + a];
+                    for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = A.buf.actions[tn * Adim + a];
                 }
             }
         }
-        __syncthreads();   // staged small parameters (state_norm statistics) are visible
+        __syncthreads();   // staged small parameters (state_norm statistics, W0 / b0) are visible
+        for (int i = tid; i < kHid * K1; i += kT) {   // layer-1 B planes from the staged W0 / b0
+            const int n = i / K1, k = i - n * K1;
+            float full = 0.0f;
+            if (k < S) full = small[kSmW0 + n * S + k];
+            else if (k == S) full = small[kSmB0 + n];
+            else if (k <= 2 * S) full = small[kSmW0 + n * S + (k - S - 1)];
+            const float hi = tc05::tf32_hi(full);
+            const uint32_t off = tc05::operand_offset(n, k, K1);
+            *reinterpret_cast<float*>(smem + kOffB1 + off) = hi;                                            // [W_hi, b_hi, W_hi, 0]
+            *reinterpret_cast<float*>(smem + kOffB1 + kB1PlaneBytes + off) = k <= S ? full - hi : 0.0f;     // [W_lo, b_lo, 0, 0]
+        }
+        TC_MARK(1);
         if (valid && net.state_avg) {
 #pragma unroll
-            for (int k = 0; k < kMaxS; ++k) if (k < S) x[k] = (x[k] - small[kSmAvg + k]) / small[kSmSd + k];
+            for (int k = 0; k < SC; ++k) if (k < S) x[k] = (x[k] - small[kSmAvg + k]) / small[kSmSd + k];
         }
-        float xrow[16];   // [X | 1 | 0] row: the B operand of G1, written into the group buffer once G2 is done with it
         {   // x~ row (K-major A operand of layer 1)
-            float xr[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) xr[k] = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kMaxS; ++k) {
+            for (int k = 0; k < SC; ++k) {
                 if (k < S) {
                     const float hi = tc05::tf32_hi(x[k]);
                     *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, k, K1)) = hi;
                     *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S + 1 + k, K1)) = x[k] - hi;
-                    xr[k] = x[k];
                 }
             }
             *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S, K1)) = 1.0f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) if (k == S) xr[k] = valid ? 1.0f : 0.0f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) xrow[k] = xr[k];
         }
         tc05::fence_proxy_async_smem();
         tc05::fence_before_thread_sync();
         __syncthreads();
 
+        TC_MARK(2);
         // ------------------------------------------------------------ layer 1 on the tensor core
         if (tid == 0) {
             tc05::fence_after_thread_sync();
@@ -282,6 +348,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
 
+        TC_MARK(3);
         // ------------------------------------------------------------ H1 = GELU(Z1): TMEM planes (layer-2 A); columns 0..31 also as
         // rows of the group buffer (B operand of the first weight-gradient pass)
 #pragma unroll 1
@@ -306,10 +373,11 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
 
+        TC_MARK(4);
         // ------------------------------------------------------------ head (64 -> OUT) on CUDA cores
-        float out[kMaxOut];
+        float out[OUTC];
 #pragma unroll
-        for (int a = 0; a < kMaxOut; ++a) out[a] = a < OUT ? small[kSmB3 + a] : 0.0f;
+        for (int a = 0; a < OUTC; ++a) out[a] = a < OUT ? small[kSmB3 + a] : 0.0f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             float z[16];
@@ -318,7 +386,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j] + small[kSmB2 + 16 * c + j]);
 #pragma unroll
-            for (int a = 0; a < kMaxOut; ++a) {
+            for (int a = 0; a < OUTC; ++a) {
                 if (a < OUT) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) out[a] = fmaf(z[j], small[kSmW3 + a * kHid + 16 * c + j], out[a]);
@@ -328,9 +396,9 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 
         // ------------------------------------------------------------ loss and d loss / d output (update.cu grads_phase, same
         // arithmetic; reference :189-204, helloworld_PPO_single_file.py:332-340 behind the variant flags)
-        float dout[kMaxOut];
+        float dout[OUTC];
 #pragma unroll
-        for (int a = 0; a < kMaxOut; ++a) dout[a] = 0.0f;
+        for (int a = 0; a < OUTC; ++a) dout[a] = 0.0f;
         float loss_c = 0.f, loss_s = 0.f, loss_e = 0.f;
         if (ni == 1) {
             const float err = out[0] - rs;
@@ -351,12 +419,12 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             if (discrete) {
                 float m = -INFINITY, sum = 0.0f;
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) if (a < OUT) m = fmaxf(m, out[a]);
+                for (int a = 0; a < OUTC; ++a) if (a < OUT) m = fmaxf(m, out[a]);
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) if (a < OUT) sum += expf(out[a] - m);
+                for (int a = 0; a < OUTC; ++a) if (a < OUT) sum += expf(out[a] - m);
                 lse = m + logf(sum);
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) {
+                for (int a = 0; a < OUTC; ++a) {
                     if (a < OUT) {
                         const float lp = out[a] - lse;
                         ent -= expf(lp) * lp;
@@ -365,7 +433,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 }
             } else {
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) {
+                for (int a = 0; a < OUTC; ++a) {
                     if (a < OUT) {
                         const float sd = expf(small[kSmStd + a]);
                         const float diff = act[a] - out[a];
@@ -402,7 +470,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             const float ge = valid ? ent_sign * A.hp.lambda_entropy * um_a * inv_bsz : 0.0f;
             if (discrete) {
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) {
+                for (int a = 0; a < OUTC; ++a) {
                     if (a < OUT) {
                         const float lp = out[a] - lse, pa = expf(lp);
                         dout[a] = gl * ((a == act_idx ? 1.0f : 0.0f) - pa) - ge * pa * (lp + ent);
@@ -410,7 +478,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 }
             } else {
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) {
+                for (int a = 0; a < OUTC; ++a) {
                     if (a < OUT) {   // OUT is uniform over the CTA: the warp-wide reduction below is convergent
                         const float sd = expf(small[kSmStd + a]);
                         const float var = sd * sd;
@@ -423,13 +491,14 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
         }
 #pragma unroll
-        for (int a = 0; a < kMaxOut; ++a) {
+        for (int a = 0; a < OUTC; ++a) {
             if (a < OUT) {
                 const float s = warp_sum(dout[a]);
                 if (lane == 0) atomicAdd(&small[kSmGB3 + a], s);
             }
         }
 
+        TC_MARK(5);
         // ------------------------------------------------------------ dZ2 = (dOut W3) * GELU'(Z2): TMEM planes + rows; dW3 by shuffles
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -442,7 +511,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 gelu_and_grad(z[j] + small[kSmB2 + 16 * c + j], gz[j], dg);
                 float dh = 0.0f;
 #pragma unroll
-                for (int a = 0; a < kMaxOut; ++a) if (a < OUT) dh = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j], dh);
+                for (int a = 0; a < OUTC; ++a) if (a < OUT) dh = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j], dh);
                 dz[j] = dh * dg;
             }
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, dz);
@@ -455,7 +524,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 if (!(lane & 1)) atomicAdd(&small[kSmGB2 + 16 * c + ((lane >> 1) & 15)], tot);
             }
 #pragma unroll
-            for (int a = 0; a < kMaxOut; ++a) {
+            for (int a = 0; a < OUTC; ++a) {
                 if (a < OUT) {
                     float w[16];
 #pragma unroll
@@ -477,6 +546,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
+        TC_MARK(6);
         // second pass: H1[:, 32:64] (recomputed from Z1, still in tensor memory) into the same group buffer -> dW2[:, 32:64]
 #pragma unroll 1
         for (int c = 2; c < 4; ++c) {
@@ -498,6 +568,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
 
+        TC_MARK(7);
         // ------------------------------------------------------------ dZ1 = dH1 * GELU'(Z1) -> rows (A operand of G1)
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -513,13 +584,18 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
             store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dh);
         }
-        if (N1 == 8) {
-            float x8[8];
+        {   // [X | 1 | 0] rows: the B operand of G1 (the group buffer is free: both passes of G2 are complete)
+            float xrow[16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x8[k] = xrow[k];
-            store_hi_lo_rows8(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, x8);
-        } else {
-            store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, xrow);
+            for (int k = 0; k < 16; ++k) xrow[k] = (k < SC && k < S) ? x[k < SC ? k : 0] : ((k == S && valid) ? 1.0f : 0.0f);
+            if (N1 == 8) {
+                float x8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x8[k] = xrow[k];
+                store_hi_lo_rows8(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, x8);
+            } else {
+                store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, xrow);
+            }
         }
         tc05::fence_proxy_async_smem();
         tc05::fence_before_thread_sync();
@@ -532,6 +608,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
 
+        TC_MARK(8);
         // ------------------------------------------------------------ gradients -> flat buffer (rows j = 16 warp + lane, lane < 16)
         const bool atomic = !persistent;   // several CTAs (tiles / the sharded path) add into a zeroed buffer
         {
@@ -587,6 +664,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
         }
 
+        TC_MARK(9);
         // ------------------------------------------------------------ clip_grad_norm_ + Adam.step
         if (sharded) {
             // ---- the gradient all-reduce, in the kernel: flags over NVLink, then ordered sums of the peers' buffers
@@ -598,12 +676,12 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                     const float4 v = ld_relaxed_sys_v4(A.px.data[r] + px_off + 4 * i4);
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
-                reinterpret_cast<float4*>(g_local)[i4] = acc;
+                reinterpret_cast<float4*>(g_smem)[i4] = acc;
             }
             for (int i = (numel & ~3) + tid; i < numel; i += kT) {
                 float acc = ld_relaxed_sys(A.px.data[0] + px_off + i);
                 for (int r = 1; r < world; ++r) acc += ld_relaxed_sys(A.px.data[r] + px_off + i);
-                g_local[i] = acc;
+                g_smem[i] = acc;
             }
             if (tid == 0) {
                 float c = 0.f, s = 0.f, e = 0.f;
@@ -623,8 +701,9 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 s_adam.bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
             }
             __syncthreads();
-            apply_net<kT>(net, A.opt[ni], s_adam, g_local, numel, A.hp.clip_grad_norm, red);
+            apply_from_smem(net, A.opt[ni], s_adam, g_smem, numel, A.hp.clip_grad_norm, red);
             __syncthreads();
+            TC_MARK(10);
         } else if (A.fused_apply) {
             __threadfence();
             __syncthreads();
@@ -632,7 +711,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             __syncthreads();
             if (s_last) {   // last CTA of this net: the whole gradient is in the buffer
                 __threadfence();
-                apply_net<kT>(net, A.opt[ni], A.adam[ni], g_local, numel, A.hp.clip_grad_norm, red);
+                apply_from_global(net, A.opt[ni], A.adam[ni], g_local, numel, A.hp.clip_grad_norm, red);
                 __syncthreads();
                 for (int i = tid; i < numel; i += kT) g_local[i] = 0.0f;
                 if (tid == 0) A.hdr->ticket[ni] = 0u;
@@ -671,9 +750,22 @@ extern "C" int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b2
 }
 
 // grid = (tiles, 2 nets).  A.update_times > 0: persistent (tiles must be 1); otherwise one minibatch.
-int b200rl_launch_update_tc(const UpdateArgs& A, int tiles, cudaStream_t stream) {
-    B200RL_CHECK_CUDA(cudaFuncSetAttribute(ppo_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    ppo_update_tc_kernel<<<dim3((unsigned)tiles, 2), kT, kSmemBytes, stream>>>(A);
+int b200rl_launch_update_tc(const UpdateArgs& A_in, int tiles, cudaStream_t stream) {
+    UpdateArgs A = A_in;
+    const char* prof = getenv("B200RL_PROFILE");   // debug: clock64 phase marks (tools/profile_update_phases.py)
+    A.profile = (prof && prof[0] == '1') ? 1 : 0;
+    const int S = A.net[0].dims[0], OUT = A.net[0].dims[3];
+    auto launch = [&](auto kern) -> int {
+        B200RL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        kern<<<dim3((unsigned)tiles, 2), kT, kSmemBytes, stream>>>(A);
+        return 0;
+    };
+    int rc;
+    if (OUT <= 1 && S <= 4) rc = launch(ppo_update_tc_kernel<1, 4>);          // Pendulum (BASELINE configs[1])
+    else if (OUT <= 2 && S <= 8) rc = launch(ppo_update_tc_kernel<2, 8>);     // LunarLanderContinuous / CartPole dims
+    else if (OUT <= 4 && S <= kMaxS) rc = launch(ppo_update_tc_kernel<4, kMaxS>);   // Hopper dims
+    else rc = launch(ppo_update_tc_kernel<kMaxOut, kMaxS>);
+    if (rc) return rc;
     B200RL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,5 +1,6 @@
-"""Debug: phase timestamps of the persistent update kernel (library built with -DB200RL_PROFILE_PHASES)."""
+"""Debug: clock64 phase marks of the persistent tcgen05 update kernel (B200RL_PROFILE=1; actor CTA, last minibatch)."""
 import os, sys
+os.environ["B200RL_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch as th
 from elegantrl_b200 import Config
@@ -15,8 +16,9 @@ agent.last_state = env.reset()[0]
 for _ in range(4):
     agent.update_net(list(agent.explore_env(env, H)))
 th.cuda.synchronize()
-marks = agent._workspace[64:64 + 14 * 8].view(th.int64).cpu().numpy()
-names = ["start", "gather done", "stage+X0 done", "fwd L0", "fwd L1", "fwd L2", "loss", "bwd l2", "bwd l1", "bwd l0", "grads done", "cluster.sync", "apply done", "zero+sync"]
-print("phase marks of CTA 0 (actor, tile 0), last minibatch; cycles since start:")
-for i in range(1, 14):
-    print(f"  {names[i]:16s} +{marks[i] - marks[i - 1]:7d}   (t = {marks[i] - marks[0]:7d})")
+marks = agent._workspace[64:64 + 11 * 8].view(th.int64).cpu().numpy()
+names = ["start", "stage params + gather", "x~ rows written", "L1 done", "H1 + L2 done", "head + loss", "dZ2 + dH1 + G2 pass 1", "G2 pass 2",
+         "dZ1 + G1", "gradients out + loss sums", "exchange + clip + Adam"]
+print("phase marks of the actor CTA, last minibatch; SM cycles:")
+for i in range(1, 11):
+    print(f"  {names[i]:28s} +{marks[i] - marks[i - 1]:7d}   (t = {marks[i] - marks[0]:7d})")
