@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--cpu-cycles", type=int, default=4, help="CPU-baseline sample size (full cycles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--total-envs", type=int, default=None, help="strong-scaling study: this many envs in total, split over the GPUs")
-    ap.add_argument("--sharded-mode", default="auto", choices=["auto", "peer", "gather", "allreduce"],
+    ap.add_argument("--sharded-mode", default="auto", choices=["auto", "peer", "peer_allreduce", "gather", "allreduce"],
                     help="N > 1: how the env shards' gradients meet (auto = in-kernel peer-memory exchange when available)")
     args = ap.parse_args()
     if args.impl == "reference":

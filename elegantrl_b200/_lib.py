@@ -140,11 +140,11 @@ SIGNATURES = {
                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200rl_workspace_error_offset": (C.c_int64, []),
     "b200rl_update_tc_supported": (C.c_int32, [C.POINTER(Net), C.POINTER(Net), C.POINTER(PPOHyper)]),
-    "b200rl_peer_exchange_floats": (C.c_int64, [C.POINTER(Net), C.POINTER(Net)]),
+    "b200rl_peer_exchange_floats": (C.c_int64, [C.POINTER(Net), C.POINTER(Net), C.c_int32, C.c_int32]),
     "b200rl_ppo_update_sharded": (C.c_int, [C.POINTER(Net), C.POINTER(Net), C.POINTER(Adam), C.POINTER(Adam),
                                             C.POINTER(TrainBuffer), C.POINTER(PPOHyper), C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
-                                            C.c_void_p, C.c_int64, C.POINTER(PeerExchange), C.c_void_p]),
+                                            C.c_void_p, C.c_int64, C.POINTER(PeerExchange), C.c_int32, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

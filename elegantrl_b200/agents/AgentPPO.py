@@ -241,15 +241,18 @@ class AgentPPO:
         self._rank, self._world = dist.get_rank(self._dist_group), dist.get_world_size(self._dist_group)
         self._px = None  # peer-memory exchange (sharded_mode "peer"): allocated at the first sharded update
 
-    def _peer_exchange(self, lib, act_desc, cri_desc):
-        """Symmetric (peer-mapped) exchange buffer + flag array of the in-kernel gradient all-reduce
-        (``b200rl_ppo_update_sharded``).  torch's symmetric-memory allocator is the plumbing: it allocates the same buffer
-        on every rank of the group and maps every peer's copy into this process (NVLink P2P)."""
-        if self._px is not None:
-            return self._px[0]
+    def _peer_exchange(self, lib, act_desc, cri_desc, update_times: int):
+        """Symmetric (peer-mapped) exchange buffer + flag array of the in-kernel exchange (``b200rl_ppo_update_sharded``).
+        torch's symmetric-memory allocator is the plumbing: it allocates the same buffer on every rank of the group and
+        maps every peer's copy into this process (NVLink P2P).  Allocated at the first sharded update (a collective: every
+        rank gets here with the same ``update_times``), again only if a later schedule needs more room."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
-        floats = int(lib.b200rl_peer_exchange_floats(C.byref(act_desc), C.byref(cri_desc)))
+        floats = int(lib.b200rl_peer_exchange_floats(C.byref(act_desc), C.byref(cri_desc), self.batch_size // self._world,
+                                                     update_times))
+        if self._px is not None and self._px[1].numel() >= floats:
+            return self._px[0]
+        old = self._px
         data = symm.empty(floats, dtype=th.float32, device=self.device)
         flags = symm.empty(_lib.PX_FLAGS, dtype=th.int32, device=self.device)
         hd, hf = symm.rendezvous(data, self._dist_group), symm.rendezvous(flags, self._dist_group)
@@ -257,32 +260,37 @@ class AgentPPO:
         flags.zero_()
         th.cuda.synchronize(self.device)
         dist.barrier(group=self._dist_group)   # every rank's flags are zero before anybody raises one
-        px = _lib.PeerExchange(rank=self._rank, world=self._world, epoch=0)
+        px = _lib.PeerExchange(rank=self._rank, world=self._world, epoch=0 if old is None else old[0].epoch,
+                               reserved=0 if old is None else old[0].reserved)
         for r in range(self._world):
             px.data[r], px.flags[r] = int(hd.buffer_ptrs[r]), int(hf.buffer_ptrs[r])
         self._px = (px, data, flags, hd, hf)
         return px
 
-    def _peer_mode(self, lib, act_desc, cri_desc, hp) -> bool:
-        """Use the in-kernel exchange?  ``sharded_mode``: "peer" (required), "auto" (default: peer when the nets have the
-        tcgen05 kernel's shape and symmetric memory can be set up, else "gather"), "gather", "allreduce"."""
+    def _peer_mode(self, lib, act_desc, cri_desc, hp, update_times: int) -> bool:
+        """Use the in-kernel exchange?  ``sharded_mode``: "peer" (record gather once per cycle) / "peer_allreduce" (gradient
+        all-reduce per minibatch), both inside the update kernel over peer memory; "auto" (default: "peer" when the nets have
+        the tcgen05 kernel's shape and symmetric memory can be set up, else "gather"); "gather", "allreduce": NCCL."""
         mode = getattr(self, "sharded_mode", "auto")
-        if mode not in ("auto", "peer"):
+        if mode not in ("auto", "peer", "peer_allreduce"):
             return False
         ok = (bool(lib.b200rl_update_tc_supported(C.byref(act_desc), C.byref(cri_desc), C.byref(hp)))
               and self.batch_size % self._world == 0 and self.batch_size // self._world <= 128 and self._world <= _lib.MAX_PEERS)
-        if ok and self._px is None:
+        if ok and mode != "peer_allreduce" and self.batch_size > 128:
+            ok = False   # the record gather runs the whole minibatch in one 128-sample tile
+        if ok:
             try:
-                self._peer_exchange(lib, act_desc, cri_desc)
+                self._peer_exchange(lib, act_desc, cri_desc, update_times)
             except Exception as err:  # noqa: BLE001
-                if mode == "peer":
+                if mode != "auto":
                     raise
                 import warnings
                 warnings.warn(f"AgentPPO: peer-memory exchange unavailable ({err!r}); using the NCCL all-gather mode")
                 self.sharded_mode = "gather"
                 return False
-        if not ok and mode == "peer":
-            raise _lib.B200RLError("sharded_mode='peer' needs S -> 64 -> 64 -> OUT GELU nets and batch_size / world <= 128")
+        if not ok and mode != "auto":
+            raise _lib.B200RLError(f"sharded_mode='{mode}' needs S -> 64 -> 64 -> OUT GELU nets and batch_size <= 128 (peer) / "
+                                   "batch_size / world <= 128 (peer_allreduce)")
         return ok
 
     # ------------------------------------------------------------------------------------- rollout
@@ -572,7 +580,7 @@ class AgentPPO:
         hp = _lib.PPOHyper(ratio_clip=float(self.ratio_clip), lambda_entropy=float(self.lambda_entropy),
                            clip_grad_norm=float(self.clip_grad_norm or 0.0), flags=int(self._ppo_flags))
         stats = th.empty(4, dtype=th.float32, device=dev)
-        peer = self._world > 1 and self._peer_mode(lib, act_desc, cri_desc, hp)
+        peer = self._world > 1 and self._peer_mode(lib, act_desc, cri_desc, hp, update_times)
         if not peer:
             if self._world > 1:
                 import torch.distributed as dist
@@ -598,8 +606,10 @@ class AgentPPO:
                                                      C.byref(tb), C.byref(hp), self.batch_size, update_times, _lib.ptr(ids), seed,
                                                      self._update_draws, _lib.ptr(stat_sums), h * n_global, count_lattice,
                                                      _lib.ptr(stats), _lib.ptr(out), _lib.ptr(workspace), workspace.numel(),
-                                                     C.byref(px), self._stream()), "ppo_update_sharded")
+                                                     C.byref(px), 0 if getattr(self, "sharded_mode", "auto") == "peer_allreduce" else 1,
+                                                     self._stream()), "ppo_update_sharded")
             px.epoch += update_times
+            px.reserved += 1
         else:
             self._update_sharded(lib, act_desc, cri_desc, act_adam, cri_adam, tb, hp, update_times, ids, out, workspace)
         self._update_draws += update_times

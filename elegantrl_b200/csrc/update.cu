@@ -601,7 +601,7 @@ int b200rl_ppo_update_sharded(const b200rl_net* actor, const b200rl_net* critic,
                               int32_t update_times, const int64_t* ids, uint64_t seed, uint64_t draw_offset,
                               const double* stat_sums, int64_t count_all, int64_t count_lattice, float* adv_stats_out,
                               float* out_scalars, void* workspace, int64_t workspace_bytes, const b200rl_peer_exchange* px,
-                              void* stream_) {
+                              int32_t exchange_mode, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200RL_REQUIRE(actor_opt && critic_opt && out_scalars && px && stat_sums, "ppo_update_sharded: NULL argument");
     B200RL_REQUIRE(px->world >= 1 && px->world <= B200RL_MAX_PEERS && px->rank >= 0 && px->rank < px->world,
@@ -620,14 +620,19 @@ int b200rl_ppo_update_sharded(const b200rl_net* actor, const b200rl_net* critic,
                    "ppo_update_sharded: nets must be S -> 64 -> 64 -> OUT GELU (b200rl_update_tc_supported)");
     A.loss_sums = A.hdr->loss_sums;
     A.fused_apply = 1;
-    A.local_batch = batch_size / px->world;
+    B200RL_REQUIRE(exchange_mode == 0 || exchange_mode == 1, "ppo_update_sharded: exchange_mode=%d", exchange_mode);
+    B200RL_REQUIRE(exchange_mode == 0 || batch_size <= 128, "ppo_update_sharded: the record gather needs batch_size <= 128 (one tile)");
+    // gradient all-reduce: each rank's tile holds its own batch_size / world samples; record gather: every rank's tile holds the
+    // whole minibatch, gathered from all ranks' exchange buffers
+    A.local_batch = exchange_mode == 1 ? batch_size : batch_size / px->world;
+    A.px_local_batch = batch_size / px->world;
     A.global_batch = batch_size;
     A.seed = seed;
     A.ids = ids;
     A.draw = draw_offset;
     A.update_times = update_times;
     A.out_scalars = out_scalars;
-    A.px_on = 1;
+    A.px_on = exchange_mode == 1 ? 2 : 1;
     A.px = *px;
     A.stat_sums = stat_sums;
     A.count_all = (double)count_all;

@@ -33,7 +33,8 @@ struct UpdateArgs {
     int grad_stride;           // floats between the two gradient buffers of the persistent kernel
     float* out_scalars;        // persistent kernel: means of the three logged scalars
     // env-sharded update with the in-kernel gradient exchange over peer memory (update_tc.cu, b200rl_ppo_update_sharded)
-    int px_on;
+    int px_on;                 // 0: single GPU; 1: gradient all-reduce per minibatch; 2: record gather once per cycle
+    int px_local_batch;        // record gather: samples per rank and minibatch
     b200rl_peer_exchange px;
     const double* stat_sums;   // this shard's advantage sums (b200rl_gae)
     double count_all, count_lat;

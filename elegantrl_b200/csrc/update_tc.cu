@@ -3,7 +3,8 @@
 // (reference AgentPPO.update_objectives, elegantrl/agents/AgentPPO.py:173-205; AgentBase.optimizer_backward,
 // elegantrl/agents/AgentBase.py:239-248); every other shape keeps the generic FP32-pipe kernels of update.cu.
 //
-// One CTA = one tile of 128 sampled transitions of ONE net (grid = tiles x 2), thread = sample = TMEM lane.  Every dense
+// One CTA = one tile of 128 sampled transitions of ONE net (grid = tiles x 2); 256 threads: warps w and w + 4 share the TMEM
+// lane quarter w % 4 (sample = lane) and split the 64 feature columns, so two threads work on every sample.  Every dense
 // contraction of the forward AND backward pass is a tcgen05 tile (3xTF32: hi / lo planes, fp32 accumulate in TMEM):
 //   L1   Z1 [128 x 64] = x~ B1^T            x~ = [x_hi, 1, x_lo, 0] (bias folded), K = round_up(2 S + 1, 8)      SS
 //   L2   Z2 [128 x 64] = H1 W2^T            H1 = GELU(Z1) as hi / lo planes in tensor memory (b2 added on read)   TS
@@ -24,8 +25,10 @@ namespace {
 
 using namespace tctrain;
 
-constexpr int kT = 128;
+constexpr int kT = 128;    // samples per tile = TMEM lanes
+constexpr int kNT = 256;   // threads: TWO per sample (warp w and w + 4 share a lane quarter and split the 64 columns)
 constexpr int kMaxS = 11, kMaxOut = 8, kK1Max = 24;
+constexpr int kAdamTab = 64;
 
 // ---- dynamic shared memory map (bytes)
 constexpr int kOffW2 = 0;                                      // W2 hi / lo K-major images (forward)
@@ -95,16 +98,16 @@ DEV void px_round(const b200rl_peer_exchange& px, int chan, uint32_t value, Work
 __device__ __noinline__ void stage_params(const b200rl_net& net, float* small, uint32_t w2_hi, uint32_t w2_lo, uint32_t wb_hi,
                                           uint32_t wb_lo, int tid, int S, int OUT, bool gaussian) {
     {
-            float4 w[8];   // W2: 4096 floats = 8 float4 per thread
+            float4 w[4];   // W2: 4096 floats = 4 float4 per thread
 #pragma unroll
-            for (int q = 0; q < 8; ++q) w[q] = __ldcg(reinterpret_cast<const float4*>(net.weight[1]) + tid + kT * q);
+            for (int q = 0; q < 4; ++q) w[q] = __ldcg(reinterpret_cast<const float4*>(net.weight[1]) + tid + kNT * q);
             // the small tensors as one index space: W0 [64 x S] | b0 | b1 | W3 [OUT x 64] | b3 | action_std_log
             const int nW0 = kHid * S, nW3 = OUT * kHid;
             const int total = nW0 + 2 * kHid + nW3 + OUT + (gaussian ? OUT : 0);
-            float sv[11];
+            float sv[6];
 #pragma unroll
-            for (int q = 0; q < 11; ++q) {
-                int idx = tid + kT * q;
+            for (int q = 0; q < 6; ++q) {
+                int idx = tid + kNT * q;
                 const float* ptr = nullptr;
                 if (idx < total) {
                     if (idx < nW0) ptr = net.weight[0] + idx;
@@ -117,8 +120,8 @@ __device__ __noinline__ void stage_params(const b200rl_net& net, float* small, u
                 sv[q] = ptr ? __ldcg(ptr) : 0.0f;
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {   // forward (K-major) and backward (MN-major) images of W2, hi / lo planes
-                const int i = 4 * (tid + kT * q), n = i >> 6, k = i & 63;
+            for (int q = 0; q < 4; ++q) {   // forward (K-major) and backward (MN-major) images of W2, hi / lo planes
+                const int i = 4 * (tid + kNT * q), n = i >> 6, k = i & 63;
                 const float v4[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
                 float h[4], l[4];
 #pragma unroll
@@ -132,8 +135,8 @@ __device__ __noinline__ void stage_params(const b200rl_net& net, float* small, u
                 st_shared_v4(wb_lo + offb, l[0], l[1], l[2], l[3]);
             }
 #pragma unroll
-            for (int q = 0; q < 11; ++q) {
-                int idx = tid + kT * q;
+            for (int q = 0; q < 6; ++q) {
+                int idx = tid + kNT * q;
                 if (idx < total) {
                     if (idx < nW0) small[kSmW0 + idx] = sv[q];
                     else if ((idx -= nW0) < kHid) small[kSmB0 + idx] = sv[q];
@@ -151,14 +154,46 @@ __device__ __noinline__ void stage_params(const b200rl_net& net, float* small, u
         }
 }
 
+// Ordered sum of the ranks' gradient buffers into shared memory.  All loads of one peer's buffer are in flight together (one
+// NVLink latency per peer instead of one per 16 bytes); the ranks are added in rank order, the same on every GPU.
+__device__ __noinline__ void px_reduce(const b200rl_peer_exchange& px, int px_off, int numel, float* g_smem) {
+    constexpr int kIt = 6;   // 6 x 256 threads x 4 floats = 6 144 >= the largest eligible net (5 456 parameters)
+    const int tid = threadIdx.x, n4 = numel >> 2;
+    float4 acc[kIt];
+    for (int r = 0; r < px.world; ++r) {
+        const float* src = px.data[r] + px_off;
+        float4 v[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int i4 = tid + kNT * it;
+            v[it] = i4 < n4 ? ld_relaxed_sys_v4(src + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            if (r == 0) acc[it] = v[it];
+            else { acc[it].x += v[it].x; acc[it].y += v[it].y; acc[it].z += v[it].z; acc[it].w += v[it].w; }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int i4 = tid + kNT * it;
+        if (i4 < n4) reinterpret_cast<float4*>(g_smem)[i4] = acc[it];
+    }
+    for (int i = (numel & ~3) + tid; i < numel; i += kNT) {
+        float a = ld_relaxed_sys(px.data[0] + px_off + i);
+        for (int r = 1; r < px.world; ++r) a += ld_relaxed_sys(px.data[r] + px_off + i);
+        g_smem[i] = a;
+    }
+}
+
 // clip + Adam of one net, out of line for the same reason (its batched loads use 64 + registers of their own)
 __device__ __noinline__ void apply_from_smem(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
                                              float clip_grad_norm, float* red) {
-    apply_net<kT, true, true>(net, opt, as, g, numel, clip_grad_norm, red);
+    apply_net<kNT, true, true>(net, opt, as, g, numel, clip_grad_norm, red);
 }
 __device__ __noinline__ void apply_from_global(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
                                                float clip_grad_norm, float* red) {
-    apply_net<kT, false, true>(net, opt, as, g, numel, clip_grad_norm, red);
+    apply_net<kNT, false, true>(net, opt, as, g, numel, clip_grad_norm, red);
 }
 
 #define TC_MARK(i) do { if (A.profile && ni == 0 && tid == 0 && u == U - 1) reinterpret_cast<long long*>(A.hdr)[8 + (i)] = clock64(); } while (0)
@@ -168,15 +203,17 @@ __device__ __noinline__ void apply_from_global(const b200rl_net& net, const b200
 // and instruction fetch was the top stall (profiles/r02_v7_update_tc_phases_before_code_size_fix.log); sized to the net it fits
 // the instruction cache.
 template <int OUTC, int SC>
-__global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_constant__ UpdateArgs A) {
+__global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_constant__ UpdateArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ float red[32];
     __shared__ AdamScalars s_adam;
+    __shared__ AdamScalars s_adam_tab[kAdamTab];   // bias corrections of the first kAdamTab minibatches, computed in parallel up front
     __shared__ int s_last;
     __shared__ uint32_t tmem_slot;
     float* small = reinterpret_cast<float*>(smem + kOffSmall);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (kT - 1), hf = tid >> 7, quarter = warp & 3;   // sample row, column half, TMEM lane quarter
     const int ni = blockIdx.y, tile = blockIdx.x;
     const b200rl_net& net = A.net[ni];
     const int S = net.dims[0], OUT = net.dims[3];
@@ -194,12 +231,19 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
     // ---- one-time setup
     if (warp == 0) tc05::tmem_alloc<512>(&tmem_slot);
     if (tid == 32) { tc05::mbar_init(bar, 1); tc05::mbar_fence_init(); }
-    for (int i = tid; i < kA1Bytes / 4; i += kT) reinterpret_cast<float*>(smem + kOffA1)[i] = 0.0f;
+    for (int i = tid; i < kA1Bytes / 4; i += kNT) reinterpret_cast<float*>(smem + kOffA1)[i] = 0.0f;
+    if (A.update_times > 0 && tid < kAdamTab && tid < A.update_times) {
+        // torch.optim.Adam bias corrections, in double like torch: one thread per minibatch instead of a serial pow() in front of
+        // every apply
+        const double step = (double)(A.opt[ni].step + tid + 1);
+        s_adam_tab[tid].step_size = (float)((double)A.opt[ni].lr / (1.0 - pow((double)A.opt[ni].beta1, step)));
+        s_adam_tab[tid].bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
+    }
     tc05::fence_before_thread_sync();
     __syncthreads();
     tc05::fence_after_thread_sync();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
+    const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);   // this warp's lane quarter
     const uint32_t w2_hi = tc05::smem_u32(smem + kOffW2), w2_lo = w2_hi + kWPlaneBytes;
     const uint32_t wb_hi = tc05::smem_u32(smem + kOffWB), wb_lo = wb_hi + kWPlaneBytes;
     const uint32_t ga_addr = tc05::smem_u32(smem + kOffGA), gb_addr = tc05::smem_u32(smem + kOffGB);
@@ -208,9 +252,11 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 
     // advantage normalisation (reference :149): from the caller's statistics, or -- env-sharded -- reduced here over the shards
     __shared__ float s_stats[2];
-    const bool sharded = A.px_on != 0;
+    // env shards: px_on == 1: gradient all-reduce per minibatch; px_on == 2: the sampled RECORDS of all minibatches are exchanged
+    // once per cycle (minibatch indices do not depend on the parameters), every rank then runs the same full-batch update
+    const bool sharded = A.px_on == 1, gathered = A.px_on == 2;
     bool normalise = A.buf.adv_stats != nullptr;
-    if (sharded && ni == 0) {
+    if ((sharded || gathered) && ni == 0) {
         if (tid < 4) reinterpret_cast<double*>(A.px.data[A.px.rank])[tid] = A.stat_sums[tid];
         px_round(A.px, 0, A.px.epoch + 1, A.hdr);
         if (tid == 0) {
@@ -237,6 +283,33 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         if (tid < 2) s_stats[tid] = A.buf.adv_stats[tid];
         __syncthreads();
     }
+    // record gather: this CTA packs ITS rank's share of every minibatch of the cycle -- {state, action, pad, unmask, logprob,
+    // normalised advantage, reward_sum}, the layout of b200rl_pack_minibatches -- into the own exchange buffer (one region per
+    // net and per cycle parity: a rank can only be one cycle ahead of a peer, cf. the flag argument in px_round), raises its flag
+    // and waits for the peers; the minibatch loop then gathers its 128 samples from all ranks' buffers with peer loads.
+    const int lb = A.px_local_batch;
+    const int px_rec_off = kPxStatFloats + ((int)(A.px.reserved & 1u) * 2 + ni) * (U * lb * rec);
+    if (gathered) {
+        float* own = A.px.data[A.px.rank] + px_rec_off;
+        const int Adim = discrete ? 1 : A.net[0].dims[3];
+        for (int i = tid; i < U * lb; i += kNT) {
+            const int uu = i / lb, sl = i - uu * lb;
+            const int64_t id = A.ids ? A.ids[i] : sample_index(A.seed, A.draw + (uint64_t)uu, (uint32_t)sl, (uint64_t)H * (uint64_t)N);
+            const int64_t tn = (id % H) * N + id / H;
+            float* r = own + (size_t)i * rec;
+            for (int k = 0; k < S; ++k) r[k] = A.buf.states[tn * S + k];
+            if (discrete) r[rec_act] = (float)reinterpret_cast<const int32_t*>(A.buf.actions)[tn];
+            else for (int a = 0; a < Adim; ++a) r[rec_act + a] = A.buf.actions[tn * Adim + a];
+            for (int k = rec_act + Adim; k < rec_tail; ++k) r[k] = 0.0f;
+            float adv = A.buf.advantages[tn];
+            if (normalise) adv = (adv - s_stats[0]) / (s_stats[1] + 1e-5f);
+            r[rec_tail + 0] = A.buf.unmasks[tn] ? 1.0f : 0.0f;
+            r[rec_tail + 1] = A.buf.logprobs[tn];
+            r[rec_tail + 2] = adv;
+            r[rec_tail + 3] = A.buf.reward_sums[tn];
+        }
+        px_round(A.px, 1 + ni, A.px.reserved + 1u, A.hdr);
+    }
 
     // flat gradient layout of this net: W0 [64 x S], b0, W1 [64 x 64], b1, W2 [OUT x 64], b2, (action_std_log)
     const int oB0 = kHid * S, oW1 = oB0 + kHid, oB1 = oW1 + kHid * kHid, oW2 = oB1 + kHid, oB2 = oW2 + OUT * kHid, oStd = oB2 + OUT;
@@ -258,13 +331,19 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         // ------------------------------------------------------------ parameters -> operand images (Adam rewrote them)
         // every load of the minibatch's parameters is issued before anything is stored: ONE L2 latency, not one per element
         TC_MARK(0);
+        // the sampled index first: its (dependent) load chain overlaps the parameter staging below
+        const int64_t* ids_u = A.ids ? A.ids + (persistent ? (size_t)u * A.local_batch : 0) : nullptr;
+        const uint64_t draw = A.draw + (uint64_t)u;
+        const int slot = tile * kT + row;   // both threads of a sample gather its scalars (the loss is evaluated redundantly)
+        const bool valid = slot < A.local_batch;
+        int64_t sampled = 0;
+        if (valid && !gathered) {
+            if (packed) sampled = ids_u ? ids_u[slot] : (int64_t)draw * A.local_batch + slot;
+            else sampled = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+        }
         stage_params(net, small, w2_hi, w2_lo, wb_hi, wb_lo, tid, S, OUT, gaussian);
 
         // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n)
-        const int64_t* ids_u = A.ids ? A.ids + (persistent ? (size_t)u * A.local_batch : 0) : nullptr;
-        const uint64_t draw = A.draw + (uint64_t)u;
-        const int slot = tile * kT + tid;
-        const bool valid = slot < A.local_batch;
         float um = 0.f, lp_old = 0.f, adv = 0.f, rs = 0.f;
         float act[OUTC];
         float x[SC];
@@ -272,11 +351,19 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         for (int a = 0; a < OUTC; ++a) act[a] = 0.0f;
 #pragma unroll
         for (int k = 0; k < SC; ++k) x[k] = 0.0f;
-        if (valid) {
+        if (valid && gathered) {   // sample `slot` of the global minibatch = record (u, slot % lb) of rank slot / lb
+            const int Adim = discrete ? 1 : A.net[0].dims[3];
+            const float* recp = A.px.data[slot / lb] + px_rec_off + (size_t)(u * lb + slot % lb) * rec;
+            const float4 tail = ld_relaxed_sys_v4(recp + rec_tail);
+            um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
+#pragma unroll
+            for (int k = 0; k < SC; ++k) if (k < S) x[k] = ld_relaxed_sys(recp + k);
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = ld_relaxed_sys(recp + rec_act + a);
+        } else if (valid) {
             const int Adim = discrete ? 1 : A.net[0].dims[3];
             if (packed) {
-                const int64_t r = ids_u ? ids_u[slot] : (int64_t)draw * A.local_batch + slot;
-                const float* recp = A.buf.states + r * rec;
+                const float* recp = A.buf.states + sampled * rec;
                 const float4 tail = *reinterpret_cast<const float4*>(recp + rec_tail);
                 um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
 #pragma unroll
@@ -284,8 +371,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
                 for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = recp[rec_act + a];
             } else {
-                const int64_t id = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
-                const int64_t tn = (id % H) * N + id / H;
+                const int64_t tn = (sampled % H) * N + sampled / H;
                 um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
                 lp_old = A.buf.logprobs[tn];
                 adv = A.buf.advantages[tn];
@@ -301,7 +387,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
         }
         __syncthreads();   // staged small parameters (state_norm statistics, W0 / b0) are visible
-        for (int i = tid; i < kHid * K1; i += kT) {   // layer-1 B planes from the staged W0 / b0
+        for (int i = tid; i < kHid * K1; i += kNT) {   // layer-1 B planes from the staged W0 / b0
             const int n = i / K1, k = i - n * K1;
             float full = 0.0f;
             if (k < S) full = small[kSmW0 + n * S + k];
@@ -317,16 +403,16 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < SC; ++k) if (k < S) x[k] = (x[k] - small[kSmAvg + k]) / small[kSmSd + k];
         }
-        {   // x~ row (K-major A operand of layer 1)
+        if (hf == 0) {   // x~ row (K-major A operand of layer 1)
 #pragma unroll
             for (int k = 0; k < SC; ++k) {
                 if (k < S) {
                     const float hi = tc05::tf32_hi(x[k]);
-                    *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, k, K1)) = hi;
-                    *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S + 1 + k, K1)) = x[k] - hi;
+                    *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(row, k, K1)) = hi;
+                    *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(row, S + 1 + k, K1)) = x[k] - hi;
                 }
             }
-            *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(tid, S, K1)) = 1.0f;
+            *reinterpret_cast<float*>(smem + kOffA1 + tc05::operand_offset(row, S, K1)) = 1.0f;
         }
         tc05::fence_proxy_async_smem();
         tc05::fence_before_thread_sync();
@@ -352,14 +438,14 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         // ------------------------------------------------------------ H1 = GELU(Z1): TMEM planes (layer-2 A); columns 0..31 also as
         // rows of the group buffer (B operand of the first weight-gradient pass)
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {   // this thread's half of the row: columns [32 hf, 32 hf + 32)
             float z[16];
             tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
             tc05::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, z);
-            if (c < 2) store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 16 * c, z);
+            if (c < 2) store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, row, 16 * c, z);
         }
         tc05::tmem_st_wait();
         tc05::fence_proxy_async_smem();
@@ -377,9 +463,9 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         // ------------------------------------------------------------ head (64 -> OUT) on CUDA cores
         float out[OUTC];
 #pragma unroll
-        for (int a = 0; a < OUTC; ++a) out[a] = a < OUT ? small[kSmB3 + a] : 0.0f;
+        for (int a = 0; a < OUTC; ++a) out[a] = 0.0f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
             float z[16];
             tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
             tc05::tmem_ld_wait();
@@ -392,6 +478,15 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                     for (int j = 0; j < 16; ++j) out[a] = fmaf(z[j], small[kSmW3 + a * kHid + 16 * c + j], out[a]);
                 }
             }
+        }
+        {   // the two halves of a row meet through shared memory (the layer-1 B planes are free once layer 1 is done); both
+            // threads then hold the full head output and evaluate the loss redundantly (fixed order: half 0 + half 1 + bias)
+            float* part = reinterpret_cast<float*>(smem + kOffB1);
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) if (a < OUT) part[(hf * kT + row) * OUTC + a] = out[a];
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) out[a] = a < OUT ? (part[row * OUTC + a] + part[(kT + row) * OUTC + a]) + small[kSmB3 + a] : 0.0f;
         }
 
         // ------------------------------------------------------------ loss and d loss / d output (update.cu grads_phase, same
@@ -485,7 +580,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                         const float diff = act[a] - out[a];
                         dout[a] = gl * diff / var;
                         const float dstd = warp_sum(gl * (diff * diff / var - 1.0f) + ge);
-                        if (lane == 0) atomicAdd(&small[kSmGStd + a], dstd);
+                        if (lane == 0 && hf == 0) atomicAdd(&small[kSmGStd + a], dstd);
                     }
                 }
             }
@@ -494,14 +589,15 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         for (int a = 0; a < OUTC; ++a) {
             if (a < OUT) {
                 const float s = warp_sum(dout[a]);
-                if (lane == 0) atomicAdd(&small[kSmGB3 + a], s);
+                if (lane == 0 && hf == 0) atomicAdd(&small[kSmGB3 + a], s);
             }
         }
 
         TC_MARK(5);
         // ------------------------------------------------------------ dZ2 = (dOut W3) * GELU'(Z2): TMEM planes + rows; dW3 by shuffles
+        if (hf != 0) { loss_c = 0.0f; loss_s = 0.0f; loss_e = 0.0f; }   // the loss sums count every sample once
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
             float z[16], gz[16], dz[16];
             tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
             tc05::tmem_ld_wait();
@@ -515,7 +611,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 dz[j] = dh * dg;
             }
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, dz);
-            store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dz);
+            store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, row, 16 * c, dz);
             {   // db2 = column sums of dZ2
                 float w[16];
 #pragma unroll
@@ -548,14 +644,16 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::fence_after_thread_sync();
         TC_MARK(6);
         // second pass: H1[:, 32:64] (recomputed from Z1, still in tensor memory) into the same group buffer -> dW2[:, 32:64]
+        if (hf == 1) {   // the threads that own columns 32..63
 #pragma unroll 1
-        for (int c = 2; c < 4; ++c) {
-            float z[16];
-            tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
-            tc05::tmem_ld_wait();
+            for (int c = 2; c < 4; ++c) {
+                float z[16];
+                tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
+                tc05::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
-            store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 16 * (c - 2), z);
+                for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+                store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, row, 16 * (c - 2), z);
+            }
         }
         tc05::fence_proxy_async_smem();
         tc05::fence_before_thread_sync();
@@ -571,7 +669,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         TC_MARK(7);
         // ------------------------------------------------------------ dZ1 = dH1 * GELU'(Z1) -> rows (A operand of G1)
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
             float dh[16], z[16];
             tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, dh);
             tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
@@ -582,9 +680,9 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 gelu_and_grad(z[j], gj, dg);
                 dh[j] *= dg;
             }
-            store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, tid, 16 * c, dh);
+            store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, row, 16 * c, dh);
         }
-        {   // [X | 1 | 0] rows: the B operand of G1 (the group buffer is free: both passes of G2 are complete)
+        if (hf == 0) {   // [X | 1 | 0] rows: the B operand of G1 (the group buffer is free: both passes of G2 are complete)
             float xrow[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xrow[k] = (k < SC && k < S) ? x[k < SC ? k : 0] : ((k == S && valid) ? 1.0f : 0.0f);
@@ -592,9 +690,9 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 float x8[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) x8[k] = xrow[k];
-                store_hi_lo_rows8(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, x8);
+                store_hi_lo_rows8(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, row, 0, x8);
             } else {
-                store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, tid, 0, xrow);
+                store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, row, 0, xrow);
             }
         }
         tc05::fence_proxy_async_smem();
@@ -609,13 +707,14 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
         tc05::fence_after_thread_sync();
 
         TC_MARK(8);
-        // ------------------------------------------------------------ gradients -> flat buffer (rows j = 16 warp + lane, lane < 16)
+        // ------------------------------------------------------------ gradients -> flat buffer (rows j = 16 quarter + lane, lane < 16;
+        // the two warps of a lane quarter take 32 columns each)
         const bool atomic = !persistent;   // several CTAs (tiles / the sharded path) add into a zeroed buffer
         {
-            const int j = 16 * warp + (lane & 15);
+            const int j = 16 * quarter + (lane & 15);
             const bool row_owner = lane < 16;
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 4 * hf; c < 4 * hf + 4; ++c) {
                 float v[8];
                 tc05::tmem_ld_32x32b_x8(tl + cG2 + 8 * c, v);
                 tc05::tmem_ld_wait();
@@ -625,13 +724,23 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 #pragma unroll
                         for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
                     } else {
+                        // 16 lanes store 16 rows of 64 floats: the same column would be a 16-way bank conflict, so lane l
+                        // stores its 8 values rotated by l (a three-stage barrel shifter of selects, no indexed registers)
+                        const int r = lane & 7;
+                        float t[8], w8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = v[i];
+                        for (int i = 0; i < 8; ++i) t[i] = (r & 1) ? v[(i + 1) & 7] : v[i];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w8[i] = (r & 2) ? t[(i + 2) & 7] : t[i];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t[i] = (r & 4) ? w8[(i + 4) & 7] : w8[i];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[(i + r) & 7] = t[i];   // t[i] = v[(i + r) & 7]
                     }
                 }
             }
 #pragma unroll 1
-            for (int c = 0; c < N1 / 8; ++c) {
+            for (int c = 0; c < (hf == 0 ? N1 / 8 : 0); ++c) {
                 float v[8];
                 tc05::tmem_ld_32x32b_x8(tl + cG1 + 8 * c, v);
                 tc05::tmem_ld_wait();
@@ -646,7 +755,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             }
         }
         __syncthreads();   // the shared-memory accumulators of the head are complete
-        for (int i = tid; i < OUT * kHid; i += kT) { if (atomic) atomicAdd(g + oW2 + i, small[kSmGW3 + i]); else g[oW2 + i] = small[kSmGW3 + i]; }
+        for (int i = tid; i < OUT * kHid; i += kNT) { if (atomic) atomicAdd(g + oW2 + i, small[kSmGW3 + i]); else g[oW2 + i] = small[kSmGW3 + i]; }
         if (tid < kHid) { if (atomic) atomicAdd(g + oB1 + tid, small[kSmGB2 + tid]); else g[oB1 + tid] = small[kSmGB2 + tid]; }
         if (tid < OUT) {
             if (atomic) atomicAdd(g + oB2 + tid, small[kSmGB3 + tid]); else g[oB2 + tid] = small[kSmGB3 + tid];
@@ -655,7 +764,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
 
         // ------------------------------------------------------------ loss sums
         {
-            const float c = block_sum<kT>(loss_c, red), s = block_sum<kT>(loss_s, red), e = block_sum<kT>(loss_e, red);
+            const float c = block_sum<kNT>(loss_c, red), s = block_sum<kNT>(loss_s, red), e = block_sum<kNT>(loss_e, red);
             if (tid == 0) {
                 if (sharded) { g[numel] = c * inv_bsz; g[numel + 1] = s * inv_bsz; g[numel + 2] = e * inv_bsz; }
                 else if (persistent) { acc_c += (double)(c * inv_bsz); acc_s += (double)(s * inv_bsz); acc_e += (double)(e * inv_bsz); }
@@ -670,19 +779,7 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             // ---- the gradient all-reduce, in the kernel: flags over NVLink, then ordered sums of the peers' buffers
             px_round(A.px, 1 + ni, A.px.epoch + 1 + (uint32_t)u, A.hdr);
             const int world = A.px.world;
-            for (int i4 = tid; i4 < (numel >> 2); i4 += kT) {
-                float4 acc = ld_relaxed_sys_v4(A.px.data[0] + px_off + 4 * i4);
-                for (int r = 1; r < world; ++r) {
-                    const float4 v = ld_relaxed_sys_v4(A.px.data[r] + px_off + 4 * i4);
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                reinterpret_cast<float4*>(g_smem)[i4] = acc;
-            }
-            for (int i = (numel & ~3) + tid; i < numel; i += kT) {
-                float acc = ld_relaxed_sys(A.px.data[0] + px_off + i);
-                for (int r = 1; r < world; ++r) acc += ld_relaxed_sys(A.px.data[r] + px_off + i);
-                g_smem[i] = acc;
-            }
+            px_reduce(A.px, px_off, numel, g_smem);
             if (tid == 0) {
                 float c = 0.f, s = 0.f, e = 0.f;
                 for (int r = 0; r < world; ++r) {
@@ -695,10 +792,13 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
             __syncthreads();
         }
         if (persistent) {
-            if (tid == 0) {   // torch.optim.Adam bias corrections of this step, in double like torch
-                const double step = (double)(A.opt[ni].step + u + 1);
-                s_adam.step_size = (float)((double)A.opt[ni].lr / (1.0 - pow((double)A.opt[ni].beta1, step)));
-                s_adam.bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
+            if (tid == 0) {
+                if (u < kAdamTab) s_adam = s_adam_tab[u];
+                else {   // long schedules: computed on the spot
+                    const double step = (double)(A.opt[ni].step + u + 1);
+                    s_adam.step_size = (float)((double)A.opt[ni].lr / (1.0 - pow((double)A.opt[ni].beta1, step)));
+                    s_adam.bc2_sqrt = (float)sqrt(1.0 - pow((double)A.opt[ni].beta2, step));
+                }
             }
             __syncthreads();
             apply_from_smem(net, A.opt[ni], s_adam, g_smem, numel, A.hp.clip_grad_norm, red);
@@ -713,13 +813,13 @@ __global__ void __launch_bounds__(kT, 1) ppo_update_tc_kernel(const __grid_const
                 __threadfence();
                 apply_from_global(net, A.opt[ni], A.adam[ni], g_local, numel, A.hp.clip_grad_norm, red);
                 __syncthreads();
-                for (int i = tid; i < numel; i += kT) g_local[i] = 0.0f;
+                for (int i = tid; i < numel; i += kNT) g_local[i] = 0.0f;
                 if (tid == 0) A.hdr->ticket[ni] = 0u;
             }
         }
     }
     if (persistent && tid == 0) {
-        if (sharded && atomicAdd(&A.hdr->pad[0], 0u) != 0u) acc_c = acc_s = acc_e = (double)nanf("");   // a peer never answered
+        if ((sharded || gathered) && atomicAdd(&A.hdr->pad[0], 0u) != 0u) acc_c = acc_s = acc_e = (double)nanf("");   // a peer never answered
         const double inv = 1.0 / (double)A.update_times;
         if (ni == 1) A.out_scalars[0] = (float)(acc_c * inv);
         else { A.out_scalars[1] = (float)(acc_s * inv); A.out_scalars[2] = (float)(acc_e * inv); }
@@ -744,9 +844,13 @@ bool b200rl_update_tc_eligible(const b200rl_net* actor, const b200rl_net* critic
 extern "C" int32_t b200rl_update_tc_supported(const b200rl_net* actor, const b200rl_net* critic, const b200rl_ppo_hyper* hyper) {
     return (actor && critic && hyper && b200rl_update_tc_eligible(actor, critic, hyper)) ? 1 : 0;
 }
-extern "C" int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b200rl_net* critic) {
+extern "C" int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b200rl_net* critic, int32_t local_batch, int32_t update_times) {
+    // gradient all-reduce: two alternating (gradient + 3 loss sums) segments per net;  record gather: two cycle parities x two
+    // nets x update_times x local_batch records of roundup4(S + A) + 4 floats
     const int seg = ((int)b200rl_net_numel(actor) + 4 + 3 & ~3) + ((int)b200rl_net_numel(critic) + 4 + 3 & ~3);
-    return kPxStatFloats + 2 * (int64_t)seg;
+    const int rec = ((actor->dims[0] + actor->dims[actor->num_linear] + 3) & ~3) + 4;
+    const int64_t grads = 2 * (int64_t)seg, records = 4 * (int64_t)update_times * local_batch * rec;
+    return kPxStatFloats + (grads > records ? grads : records);
 }
 
 // grid = (tiles, 2 nets).  A.update_times > 0: persistent (tiles must be 1); otherwise one minibatch.
@@ -757,7 +861,7 @@ int b200rl_launch_update_tc(const UpdateArgs& A_in, int tiles, cudaStream_t stre
     const int S = A.net[0].dims[0], OUT = A.net[0].dims[3];
     auto launch = [&](auto kern) -> int {
         B200RL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        kern<<<dim3((unsigned)tiles, 2), kT, kSmemBytes, stream>>>(A);
+        kern<<<dim3((unsigned)tiles, 2), kNT, kSmemBytes, stream>>>(A);
         return 0;
     };
     int rc;

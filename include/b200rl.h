@@ -241,19 +241,26 @@ B200RL_API int b200rl_ppo_apply(const b200rl_net* actor, const b200rl_net* criti
  * gather (elegantrl/train/run.py:305-320).  Nets must have the shape b200rl_update_tc_supported accepts.
  *   data[r] / flags[r]: rank r's exchange buffer (b200rl_peer_exchange_floats floats) / flag array (B200RL_PX_FLAGS
  *   uint32, zero-initialised once) as mapped into THIS process (symmetric allocation; data[rank] is the own one).
- *   epoch: flags written by this call are epoch + 1 ... epoch + update_times; the caller advances it by update_times. */
+ *   epoch: flags written by this call are epoch + 1 ... epoch + update_times; the caller advances it by update_times.
+ * exchange_mode 0 is the above; exchange_mode 1 (batch_size <= 128) exchanges DATA instead of gradients, once per call: the
+ * minibatch indices do not depend on the parameters, so every rank packs its share of ALL minibatches of this update_net
+ * (update_times x batch_size / world records, the layout of b200rl_pack_minibatches, advantages already normalised with the
+ * exchanged statistics) into its exchange buffer, one flag round makes them visible, and every rank runs the identical
+ * full-minibatch update, gathering its 128 samples from all ranks' buffers with peer loads -- two flag rounds per cycle
+ * instead of one per minibatch, no reduction, replicas bit-identical by construction. */
 #define B200RL_MAX_PEERS 8
 #define B200RL_PX_FLAGS 64
 typedef struct b200rl_peer_exchange {
     int32_t rank, world;
     float* data[B200RL_MAX_PEERS];
     uint32_t* flags[B200RL_MAX_PEERS];
-    uint32_t epoch;
-    uint32_t reserved;
+    uint32_t epoch;                       /* minibatches exchanged so far (gradient mode); the caller advances it */
+    uint32_t reserved;                    /* update_net calls so far (record mode: flag value and buffer parity); caller advances */
 } b200rl_peer_exchange;
 B200RL_API int64_t b200rl_workspace_error_offset(void);
 B200RL_API int32_t b200rl_update_tc_supported(const b200rl_net* actor, const b200rl_net* critic, const b200rl_ppo_hyper* hyper);
-B200RL_API int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b200rl_net* critic);
+B200RL_API int64_t b200rl_peer_exchange_floats(const b200rl_net* actor, const b200rl_net* critic, int32_t local_batch,
+                                               int32_t update_times);
 /* batch_size is the GLOBAL minibatch (a multiple of world, <= 128 * world); ids: [update_times, batch_size / world] local
  * indices or NULL.  stat_sums: this shard's device double[4] from b200rl_gae; count_all / count_lattice as b200rl_adv_stats
  * (global counts); adv_stats_out: device float[4], receives {mean, std, 1 / (std + 1e-5), 0}.  buffer->adv_stats is ignored
@@ -266,7 +273,7 @@ B200RL_API int b200rl_ppo_update_sharded(const b200rl_net* actor, const b200rl_n
                                          const int64_t* ids, uint64_t seed, uint64_t draw_offset, const double* stat_sums,
                                          int64_t count_all, int64_t count_lattice, float* adv_stats_out, float* out_scalars,
                                          void* workspace, int64_t workspace_bytes, const b200rl_peer_exchange* px,
-                                         void* stream);
+                                         int32_t exchange_mode, void* stream);
 
 /* out_scalars[i] = loss_sums[i] / update_times (after the caller all-reduced loss_sums if sharded). */
 B200RL_API int b200rl_loss_means(const double* loss_sums, int32_t update_times, float* out_scalars, void* stream);

@@ -36,7 +36,7 @@ def main():
     global_ids = np.concatenate([(env_l[r] + r * shard) * h + t_l[r] for r in range(world)], axis=1)  # [updates, batch]
 
     keys = ("states", "actions", "logprobs", "rewards", "undones", "unmasks")
-    modes = ("peer", "gather", "allreduce") if tuple(int(x) for x in g["dims"][4:]) == (64, 64) else ("gather", "allreduce")
+    modes = ("peer", "peer_allreduce", "gather", "allreduce") if tuple(int(x) for x in g["dims"][4:]) == (64, 64) else ("gather", "allreduce")
     for mode in modes:
         run_mode(mode, g, rank, world, local, dev, h, n, shard, lo, batch, updates, local_ids, global_ids, keys)
     dist.barrier()
