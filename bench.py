@@ -230,13 +230,18 @@ def run_engine(args):
     host_last_state = th.empty((n_envs, 3), dtype=th.float32).pin_memory()
     host_in.copy_(env.engine_state_block())
 
+    copy_stream = th.cuda.Stream(device=dev)   # the D2H copies ride beside GAE + update instead of in front of them
+
     def cycle_e2e():
         block = env.engine_state_block()
         block.copy_(host_in, non_blocking=True)              # H2D: the step's inputs from pinned host memory
         buffer = agent.explore_env(env, HORIZON)             # public API
-        host_last_state.copy_(agent.last_state, non_blocking=True)   # D2H: final once the rollout is done (stream order)
-        host_in.copy_(block, non_blocking=True)              # D2H: env state for the host-side loop
+        copy_stream.wait_stream(th.cuda.current_stream())    # ... after the rollout
+        with th.cuda.stream(copy_stream):
+            host_last_state.copy_(agent.last_state, non_blocking=True)   # D2H: final state of the rollout
+            host_in.copy_(block, non_blocking=True)          # D2H: env state for the host-side loop
         result = agent.update_net(list(buffer))              # public API: returns 3 Python floats (D2H + sync)
+        copy_stream.synchronize()                            # the host owns host_in / host_last_state from here on
         return result
 
     for _ in range(max(args.warmup, 3)):

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200rl.so")
-SOURCES = ["api.cu", "forward.cu", "gae.cu", "update.cu", "update_tc.cu", "sac.cu", "rollout.cu", "rollout_tc.cu", "rollout_ts.cu"]
+SOURCES = ["api.cu", "forward.cu", "forward_tc.cu", "gae.cu", "update.cu", "update_tc.cu", "sac.cu", "rollout.cu", "rollout_tc.cu", "rollout_ts.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -128,6 +128,8 @@ class AgentPPO:
         self._desc_cache = {}        # id(module) -> (parameter pointers, descriptor)
         self._dist_group = None      # set by enable_data_parallel()
         self._px = None
+        self._host_result = None     # pinned host block the update kernel writes the three logged scalars to
+        self.pinned_result = True
         self._rank, self._world = 0, 1
         self.last_update_info = {}
         self.cuda_graph_rollout = bool(getattr(args, "cuda_graph_rollout", False))  # external envs: see _explore_vec_env_graphed
@@ -140,7 +142,7 @@ class AgentPPO:
         """The agent may be pickled (multiprocessing): raw handles, pointer blocks and CUDA graphs are per process."""
         state = dict(self.__dict__)
         state.update(_lib_handle=None, _fused_pre=None, _rollout_args=None, _desc_cache={}, _rollout_graphs={},
-                     _workspace=None, _value_cache=None, _px=None, _dist_group=None)
+                     _workspace=None, _value_cache=None, _px=None, _dist_group=None, _host_result=None)
         return state
 
     def _require_engine(self):
@@ -539,7 +541,19 @@ class AgentPPO:
     def update_net(self, buffer) -> Tuple[float, float, float]:
         """Reference AgentPPO.update_net (AgentPPO.py:135-171): returns (obj_critic, obj_actor, obj_entropy)
         averaged over ``update_times = int(H * repeat_times / batch_size)`` minibatch updates."""
-        obj_critic, obj_actor, obj_entropy = self.update_net_device(buffer).tolist()  # the one D2H copy of the cycle
+        # The three scalars are the one device -> host read of the cycle.  The update kernel stores them straight into pinned
+        # host memory (unified addressing: a cudaHostAlloc'ed block is device-accessible at the same address), so the host
+        # only waits for the stream -- no copy-engine round trip behind the last kernel.
+        self._require_engine()
+        host = self._host_result if self.pinned_result else None
+        if host is None and self.pinned_result:
+            host = self._host_result = th.empty(3, dtype=th.float32).pin_memory()
+        if host is not None:
+            self.update_net_device(buffer, _out=host)
+            th.cuda.current_stream(self.device).synchronize()
+            obj_critic, obj_actor, obj_entropy = host.tolist()
+        else:
+            obj_critic, obj_actor, obj_entropy = self.update_net_device(buffer).tolist()
         if obj_critic != obj_critic and getattr(self, "_px", None) is not None:   # NaN: did a peer fail to answer?
             off = int(_lib.load().b200rl_workspace_error_offset())
             if int(self._workspace[off:off + 4].view(th.int32).item()) != 0:
@@ -547,8 +561,9 @@ class AgentPPO:
         return obj_critic, obj_actor, obj_entropy
 
     @_on_device
-    def update_net_device(self, buffer) -> TEN:
-        """``update_net`` without the host synchronisation: the three scalars stay in a device tensor."""
+    def update_net_device(self, buffer, _out: Optional[TEN] = None) -> TEN:
+        """``update_net`` without the host synchronisation: the three scalars stay in a device tensor (or go to ``_out``,
+        three floats of device-accessible memory)."""
         lib = self._require_engine()
         states, actions, logprobs, rewards, undones, unmasks = buffer
         h, n = states.shape[0], states.shape[1]
@@ -591,7 +606,7 @@ class AgentPPO:
                               logprobs=_lib.ptr(self._check(logprobs, "logprobs")), advantages=_lib.ptr(advantages),
                               reward_sums=_lib.ptr(reward_sums), adv_stats=_lib.ptr(stats), horizon_len=h, num_envs=n,
                               discrete_actions=int(self._categorical))
-        out = th.empty(3, dtype=th.float32, device=dev)
+        out = th.empty(3, dtype=th.float32, device=dev) if _out is None else _out
         ids = getattr(self, "_inject_ids", None)
         if self._world == 1:
             _lib.check(lib.b200rl_ppo_update(C.byref(act_desc), C.byref(cri_desc), C.byref(act_adam), C.byref(cri_adam),
@@ -732,8 +747,10 @@ class AgentA2C(AgentPPO):
     def __init__(self, net_dims, state_dim: int, action_dim: int, gpu_id: int = 0, args=None):
         super().__init__(net_dims, state_dim, action_dim, gpu_id, args)
         self._ppo_flags = _lib.PPO_A2C | _lib.PPO_ACTOR_UNMASKED
+        self.pinned_result = False   # the third slot is patched on the device below (stream-ordered)
 
-    def update_net_device(self, buffer) -> TEN:
+    def update_net_device(self, buffer, _out: Optional[TEN] = None) -> TEN:
+        assert _out is None
         assert buffer[0].shape[1] == 1, "AgentA2C follows the reference: single-env buffers [H, 1, ...] only"
         lambda_entropy, self.lambda_entropy = self.lambda_entropy, 0.0  # the A2C objective has no entropy term
         try:

@@ -3,23 +3,16 @@
 //   b200rl_policy_step  : ActorPPO.get_action + convert_action_for_env (+ critic value)
 //                         (reference AgentPPO.py:368-376, 388-390; loop body of _explore_vec_env :113-119)
 #include "mlp_tile.cuh"
+#include "policy_epilogue.cuh"
+
+// forward_tc.cu: the tcgen05 kernel for S -> 64 -> 64 -> OUT GELU nets
+bool b200rl_forward_tc_eligible(const b200rl_net* net);
+int b200rl_launch_forward_tc(int policy, const b200rl_net* net, const float* x, int64_t rows, float* out, int out_tanh,
+                             const PolicyOut& po, cudaStream_t stream);
 
 namespace {
 
 constexpr int kFwdThreads = 256;
-
-enum { kPlain = 0, kGaussian = 1, kCategorical = 2 };  // epilogue of mlp_forward_kernel
-
-struct PolicyOut {
-    const float* eps;  // [rows, A] or nullptr (Gaussian: N(0,1); categorical: Exp(1))
-    uint64_t seed, step;
-    const uint64_t* step_base;  // optional device counter added to `step` (CUDA-graph replays)
-    int64_t env_offset;
-    float* action;
-    float* logprob;
-    float* env_action;
-    int32_t* action_index;  // categorical
-};
 
 template <int TB, int POLICY>
 __global__ void __launch_bounds__(kFwdThreads)
@@ -51,61 +44,13 @@ mlp_forward_kernel(const __grid_constant__ b200rl_net net, const float* __restri
                 out[row * J + j] = out_tanh ? tanhf(v) : v;
             }
         }
-    } else if (POLICY == kCategorical) {
-        // ActorDiscretePPO.get_action (reference AgentPPO.py:407-413): softmax -> Categorical.sample() -> log_prob.
-        // torch.multinomial's one-draw path is argmax(p / q), q ~ Exp(1); the first maximum wins ties (argmax).
-        const int b = threadIdx.x;
-        const int64_t row = row0 + b;
-        if (b < TB && row < rows) {
-            float m = -INFINITY;
-            for (int a = 0; a < J; ++a) m = fmaxf(m, cur[T::elem(a, b)]);
-            float sum = 0.0f;
-            for (int a = 0; a < J; ++a) sum += expf(cur[T::elem(a, b)] - m);
-            const float inv_sum = 1.0f / sum;
-            float best = -1.0f, best_p = 0.0f;
-            int best_a = 0;
-            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
-            for (int a = 0; a < J; ++a) {
-                const float p = expf(cur[T::elem(a, b)] - m) * inv_sum;
-                float q;
-                if (po.eps) {
-                    q = po.eps[row * J + a];
-                } else {
-                    if ((a & 3) == 0) bits = rollout_bits(po.seed, (uint64_t)(po.env_offset + row), rng_step, (uint32_t)(a >> 2));
-                    const uint32_t w = (a & 3) == 0 ? bits.x : (a & 3) == 1 ? bits.y : (a & 3) == 2 ? bits.z : bits.w;
-                    q = -logf(u32_to_unit_open(w));
-                }
-                const float race = __fdiv_rn(p, q);
-                if (race > best) { best = race; best_a = a; best_p = p; }
-            }
-            po.action_index[row] = best_a;
-            po.logprob[row] = logf(best_p);
-        }
     } else {
-        // a = mu + sigma * eps; logprob = sum_a Normal(mu, sigma).log_prob(a)   (torch op order, no contraction)
         const int b = threadIdx.x;
         const int64_t row = row0 + b;
         if (b < TB && row < rows) {
-            float logp = 0.0f;
-            for (int a = 0; a < J; ++a) {
-                float mu = cur[T::elem(a, b)];
-                float sd = expf(net.action_std_log[a]);
-                float e;
-                if (po.eps) {
-                    e = po.eps[row * J + a];
-                } else {
-                    RolloutNoise nz = rollout_noise(po.seed, (uint64_t)(po.env_offset + row), rng_step, (uint32_t)(a >> 1));
-                    e = (a & 1) ? nz.normal.y : nz.normal.x;
-                }
-                float act = __fadd_rn(__fmul_rn(e, sd), mu);
-                float diff = __fsub_rn(act, mu);
-                float var = __fmul_rn(sd, sd);
-                float lp = __fsub_rn(__fsub_rn(-__fdiv_rn(__fmul_rn(diff, diff), __fmul_rn(2.0f, var)), logf(sd)), kLogSqrt2Pi);
-                logp = __fadd_rn(logp, lp);
-                po.action[row * J + a] = act;
-                po.env_action[row * J + a] = tanhf(act);
-            }
-            po.logprob[row] = logp;
+            auto get = [&](int a) { return cur[T::elem(a, b)]; };
+            if (POLICY == kCategorical) categorical_epilogue(po, rng_step, row, J, get);
+            else gaussian_epilogue(net, po, rng_step, row, J, get);
         }
     }
 }
@@ -114,6 +59,7 @@ template <int POLICY>
 int launch_forward(const b200rl_net* net, const float* x, int64_t rows, float* out, int out_tanh, const PolicyOut& po,
                    cudaStream_t stream) {
     if (rows <= 0) return 0;
+    if (b200rl_forward_tc_eligible(net)) return b200rl_launch_forward_tc(POLICY, net, x, rows, out, out_tanh, po, stream);
     const int maxdim = b200rl_net_maxdim(net);
     // 64-sample tiles when two ping-pong buffers fit comfortably, else 32
     if (maxdim <= 256) {

@@ -42,7 +42,9 @@ constexpr int kWorkerWarps = 14, kIssuerWarps = kTiles;
 //   4  one arrival per 32 hidden units instead of per 16 (half the arrivals / issuer wake-ups; 8 UMMAs per wake-up)
 //   8  the state row of step t is stored while the actor's last UMMAs run (it is known at the start of the step)
 constexpr int kDefaultVariant = 2;   // profiles/r02_v3_rollout_ts_variants.log
-constexpr int kVarPrefetch = 1, kVarIssuerPlace = 2, kVarArrive2 = 4, kVarEarlyStore = 8;
+//  16  experiment: the critic is NOT evaluated inside the time loop (values / last_value are left unwritten) -- measures what an
+//      actor-only loop + a separate throughput-bound values pass over the stored states could gain
+constexpr int kVarPrefetch = 1, kVarIssuerPlace = 2, kVarArrive2 = 4, kVarEarlyStore = 8, kVarNoCritic = 16;
 template <int V> constexpr int warps_of() { return (V & kVarIssuerPlace) ? 20 : kWorkerWarps + kIssuerWarps; }
 constexpr int kTileCols = 128;   // TMEM columns per tile: X [0, 64) + D [64, 128)
 
@@ -86,6 +88,7 @@ DEV void load_small(const b200rl_net& net, float* sm) {
 template <int V>
 __global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_kernel(const __grid_constant__ RolloutParams P) {
     constexpr bool kPrefetch = (V & kVarPrefetch) != 0, kArrive2 = (V & kVarArrive2) != 0, kEarly = (V & kVarEarlyStore) != 0;
+    constexpr bool kCritic = (V & kVarNoCritic) == 0;
     constexpr int kThreads = warps_of<V>() * 32;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* small = reinterpret_cast<float*>(smem + kOffSmall);
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_ker
             for (int t = 0; t <= H; ++t) {
                 tc05::mbar_wait(&b[0], t & 1);             // x~(t) of both nets is in shared memory
                 if (t < H) evaluate(nd_a, a1_a);
-                evaluate(nd_c, a1_c);
+                if (kCritic) evaluate(nd_c, a1_c);
             }
         }
     } else {
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_ker
                 if (norm_a) { xa[0] = (o0 - sm_a[kAvg]) / sm_a[kStd]; xa[1] = (o1 - sm_a[kAvg + 1]) / sm_a[kStd + 1]; xa[2] = (o2 - sm_a[kAvg + 2]) / sm_a[kStd + 2]; }
                 if (norm_c) { xc[0] = (o0 - sm_c[kAvg]) / sm_c[kStd]; xc[1] = (o1 - sm_c[kAvg + 1]) / sm_c[kStd + 1]; xc[2] = (o2 - sm_c[kAvg + 2]) / sm_c[kStd + 2]; }
                 write_x_row(a1_act, row, xa);
-                write_x_row(a1_cri, row, xc);
+                if (kCritic) write_x_row(a1_cri, row, xc);
                 tc05::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(&b[0]);
@@ -290,9 +293,11 @@ __global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_ker
                     logprob = __fsub_rn(__fsub_rn(-__fdiv_rn(__fmul_rn(diff, diff), var2), log_sd), kLogSqrt2Pi);
                 }
                 // -------------------------------------------------------------------- critic: V(s_t)
-                tc05::mbar_wait(&b[1], ph & 1);
-                tc05::fence_after_thread_sync();
-                hidden();
+                if (kCritic) {
+                    tc05::mbar_wait(&b[1], ph & 1);
+                    tc05::fence_after_thread_sync();
+                    hidden();
+                }
                 // state row of step t (or last_state)
                 if (!kEarly || last) store_state_row(last ? P.last_state : P.states + (size_t)t * N * 3, obs0, obs1, obs2);
                 if (!last) {
@@ -334,14 +339,16 @@ __global__ void __launch_bounds__(warps_of<V>() * 32, 1) rollout_pendulum_ts_ker
                         P.undones[rowbase + n] = 1;
                     }
                 }
-                tc05::mbar_wait(&b[2], ph & 1);
-                tc05::fence_after_thread_sync();
-                const float val = head(sm_c);
-                tc05::fence_before_thread_sync();
-                ph += 1;
-                if (live) {
-                    if (!last) { if (P.values) P.values[rowbase + n] = val; }
-                    else if (P.last_value) P.last_value[n] = val;
+                if (kCritic) {
+                    tc05::mbar_wait(&b[2], ph & 1);
+                    tc05::fence_after_thread_sync();
+                    const float val = head(sm_c);
+                    tc05::fence_before_thread_sync();
+                    ph += 1;
+                    if (live) {
+                        if (!last) { if (P.values) P.values[rowbase + n] = val; }
+                        else if (P.last_value) P.last_value[n] = val;
+                    }
                 }
             }
             if (live) { P.theta[n] = theta; P.theta_dot[n] = theta_dot; P.cur_step[n] = cur_step; }
@@ -392,6 +399,7 @@ int b200rl_launch_rollout_ts(const RolloutParams& P_in, cudaStream_t stream) {
         case 11: return launch_variant<11>(P, stream);
         case 13: return launch_variant<13>(P, stream);
         case 15: return launch_variant<15>(P, stream);
+        case 18: return launch_variant<18>(P, stream);
         default: break;
     }
     b200rl_set_error("rollout_ts: B200RL_TS_VARIANT=%s is not built", v);

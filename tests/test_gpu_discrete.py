@@ -22,8 +22,18 @@ def update_impl(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(params=["tc", "ffma"])
+def forward_impl(request, monkeypatch):
+    """tcgen05 forward kernel (64 x 64 GELU nets, csrc/forward_tc.cu) / CUDA-core kernel for every shape (csrc/forward.cu)"""
+    if request.param == "ffma":
+        monkeypatch.setenv("B200RL_FORWARD", "ffma")
+    else:
+        monkeypatch.delenv("B200RL_FORWARD", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", gu.DISCRETE_CASES)
-def test_policy_step_discrete_injected_noise(case):
+def test_policy_step_discrete_injected_noise(case, forward_impl):
     """b200rl_policy_step_discrete with torch.multinomial's Exp(1) noise replayed: sampled indices bit-exact."""
     g = gu.load(case)
     agent = G.discrete_agent_from_golden(g)
@@ -39,7 +49,7 @@ def test_policy_step_discrete_injected_noise(case):
     G.assert_close(ent, g["nets.entropy"], RTOL, 1e-6)
 
 
-def test_policy_step_discrete_philox_statistics():
+def test_policy_step_discrete_philox_statistics(forward_impl):
     """Device RNG: the empirical action frequencies of 400 000 draws follow softmax(logits); log-probs match the drawn index."""
     g = gu.load(gu.DISCRETE_CASES[-1])
     agent = G.discrete_agent_from_golden(g)

@@ -104,3 +104,38 @@ def test_both_rollout_kernels_agree_at_full_size(monkeypatch):
     for other in ("tc", "ts"):
         for a, b in zip(res[other], res["ffma"]):
             np.testing.assert_allclose(a, b, rtol=1e-4, atol=2e-5)
+
+
+def test_fused_rollout_native_noise_statistics(rollout_impl):
+    """The fused kernels draw their N(0,1) / U(0,1) numbers from the same ``rollout_noise()`` as the per-step kernel but with
+    the counter laid out as (env, step_offset + t): recover the noise from the stored trajectory (z = (a - mu(s)) / sigma, mu
+    from torch's fp32 MLP) and check its moments, its independence across envs, across consecutive time steps and
+    across consecutive rollouts (the step offset advances by H), and the reset draws (uniform in [-pi, pi) x [-1, 1))."""
+    agent, env = make(seed=11)
+    sd = float(th.exp(agent.act.action_std_log[0]))
+    zs = []
+    for _ in range(2):
+        states, actions, logprobs, _, _, unmasks = agent.explore_env(env, H)
+        with th.no_grad():   # torch fp32 mean on the stored states (TF32 off by default for matmul)
+            mu = agent.act.net(agent.act.state_norm(states.reshape(-1, 3))).reshape(H, N)
+        zs.append(((actions[..., 0] - mu) / sd).double())
+        trunc = ~unmasks
+    z = zs[0]
+    assert abs(float(z.mean())) < 2e-3 and abs(float(z.std()) - 1.0) < 2e-3
+    assert abs(float((z ** 3).mean())) < 6e-3 and abs(float((z ** 4).mean()) - 3.0) < 2e-2
+    corr = lambda a, b: float(((a - a.mean()) * (b - b.mean())).mean() / (a.std() * b.std()))
+    assert abs(corr(z[:-1], z[1:])) < 2e-3            # consecutive time steps of the same env
+    assert abs(corr(z[:, :-1], z[:, 1:])) < 2e-3      # neighbouring envs at the same step
+    assert abs(corr(z[:-7, :-5], z[7:, 5:])) < 2e-3   # a diagonal of the (step, env) counter lattice
+    assert abs(corr(zs[0], zs[1])) < 2e-3             # the next rollout continues the stream (step_offset += H)
+    assert not th.equal(zs[0], zs[1])
+    # tail mass: P(|z| > 3) = 2.6998e-3
+    assert abs(float((z.abs() > 3).double().mean()) - 2.6998e-3) < 2e-4
+    # reset draws of the second rollout: the state after a truncation is (cos, sin)(theta0), theta_dot0 with theta0 ~ U(-pi, pi), theta_dot0 ~ U(-1, 1)
+    t_i, n_i = th.nonzero(trunc[:-1], as_tuple=True)
+    nxt = states[t_i + 1, n_i]
+    theta0, thd0 = th.atan2(nxt[:, 1], nxt[:, 0]).double(), nxt[:, 2].double()
+    assert len(theta0) > 20000
+    assert abs(float(theta0.mean())) < 0.05 and abs(float(theta0.std()) - np.pi / np.sqrt(3)) < 0.03
+    assert abs(float(thd0.mean())) < 0.02 and abs(float(thd0.std()) - 1 / np.sqrt(3)) < 0.01 and float(thd0.abs().max()) <= 1.0
+    assert abs(corr(theta0, thd0)) < 0.02

@@ -19,8 +19,19 @@ RTOL = 1e-4
 
 
 # ------------------------------------------------------------------------------------------- nets
+@pytest.fixture(params=["tc", "ffma"])
+def forward_impl(request, monkeypatch):
+    """S -> 64 -> 64 -> OUT GELU nets take the tcgen05 forward kernel (csrc/forward_tc.cu); B200RL_FORWARD=ffma forces the
+    CUDA-core kernel (csrc/forward.cu), which every other shape uses anyway."""
+    if request.param == "ffma":
+        monkeypatch.setenv("B200RL_FORWARD", "ffma")
+    else:
+        monkeypatch.delenv("B200RL_FORWARD", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", gu.SYNTH_CASES)
-def test_mlp_forward(case):
+def test_mlp_forward(case, forward_impl):
     g = gu.load(case)
     agent = G.agent_from_golden(g)
     lib = _lib.load()
@@ -39,9 +50,10 @@ def test_mlp_forward(case):
         G.assert_close(agent.act(state), g["nets.actor_forward"], RTOL, 2e-6)
 
 
-@pytest.mark.parametrize("rows", [1, 31, 64, 65, 1000])
-def test_mlp_forward_ragged_rows(rows):
-    g = gu.load("synth_s8_a2_128x64")
+@pytest.mark.parametrize("rows", [1, 31, 64, 65, 127, 128, 129, 1000, 40001])
+@pytest.mark.parametrize("case", ["synth_s8_a2_128x64", "synth_s8_a2_64x64"])
+def test_mlp_forward_ragged_rows(rows, case):
+    g = gu.load(case)
     agent = G.agent_from_golden(g)
     rng = np.random.default_rng(rows)
     state = rng.standard_normal((rows, 8)).astype(np.float32)
@@ -60,8 +72,29 @@ def test_mlp_forward_wide_net():
     G.assert_close(agent.get_values(state), want, RTOL, 2e-6)
 
 
+def test_forward_tc_against_ffma_many_tiles(monkeypatch):
+    """The persistent tcgen05 forward kernel (296 CTAs walking 128-row tiles) against the CUDA-core kernel on 100 003 rows
+    (782 tiles, ragged tail), S = 11 / A = 3: values, means, and the injected-noise policy step."""
+    g = gu.load("synth_s11_a3_64x64")
+    agent = G.agent_from_golden(g)
+    rng = np.random.default_rng(5)
+    rows = 100_003
+    state = G.cuda(rng.standard_normal((rows, 11)).astype(np.float32) * 2.0)
+    eps = G.cuda(rng.standard_normal((rows, 3)).astype(np.float32))
+    res = {}
+    for impl in ("tc", "ffma"):
+        if impl == "ffma":
+            monkeypatch.setenv("B200RL_FORWARD", "ffma")
+        res[impl] = (agent.get_values(state).clone(),) + tuple(t.clone() for t in agent._policy_step(state, eps=eps))
+    for a, b in zip(res["tc"], res["ffma"]):
+        G.assert_close(a, b.cpu().numpy(), RTOL, 1e-5)
+    sub = rng.integers(0, rows, 200)
+    want = po.critic_value(gu.net_of(g, "critic"), state[sub].cpu().numpy())
+    G.assert_close(res["tc"][0][sub], want, RTOL, 2e-6)
+
+
 @pytest.mark.parametrize("case", gu.SYNTH_CASES)
-def test_policy_step_injected_noise(case):
+def test_policy_step_injected_noise(case, forward_impl):
     g = gu.load(case)
     agent = G.agent_from_golden(g)
     state = g["nets.state"]
@@ -86,8 +119,9 @@ def test_policy_step_injected_noise(case):
     G.assert_close(logprob_g, g["nets.logprob"], RTOL, floor)
 
 
-def test_policy_step_philox_statistics():
-    g = gu.load("synth_s8_a2_128x64")
+@pytest.mark.parametrize("case", ["synth_s8_a2_128x64", "synth_s8_a2_64x64"])
+def test_policy_step_philox_statistics(case):
+    g = gu.load(case)
     agent = G.agent_from_golden(g)
     rows = 200_000
     state = th.zeros((rows, 8), device="cuda:0")

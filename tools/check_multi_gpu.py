@@ -26,7 +26,13 @@ def main():
     case = os.environ.get("CHECK_CASE", "synth_s8_a2_64x64")   # 64 x 64 nets: the tcgen05 update kernel + peer exchange apply
     g = gu.load(case)
     h, n = g["buf.states"].shape[:2]
-    assert n % world == 0
+    if n % world:   # envs are independent columns: drop the remainder so that every rank owns the same number of envs
+        n -= n % world
+        assert n > 0, f"{case} has fewer envs than ranks"
+        for k in list(g.keys()):
+            if k.startswith("buf.") and g[k].ndim >= 2 and g[k].shape[0] == h:
+                g[k] = np.ascontiguousarray(g[k][:, :n])
+        g["buf.last_state"] = np.ascontiguousarray(g["buf.last_state"][:n])
     shard = n // world
     lo = rank * shard
     batch, updates = 16 * world, 3
