@@ -96,9 +96,9 @@ DEV float ld_grad(const float* p) { return GSMEM ? *p : __ldcg(p); }
 template <bool GSMEM>
 DEV float4 ld_grad4(const float4* p) { return GSMEM ? *p : __ldcg(p); }
 
-template <int NT, bool GSMEM = false, bool FAST = false>
-DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
-                   float clip_grad_norm, float* red, int part = 0, int nparts = 1) {
+// clip_grad_norm_'s scale factor for one net's gradient (the whole CTA takes part)
+template <int NT, bool GSMEM>
+DEV float clip_coef(const float* g, int numel, float clip_grad_norm, float* red) {
     // squared norm of the whole gradient: batches of 8 independent L2 loads per thread (a plain loop would wait for
     // one ~700-cycle load per iteration)
     float ss = 0.0f;
@@ -109,9 +109,14 @@ DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScal
 #pragma unroll
         for (int q = 0; q < 8; ++q) ss = fmaf(v[q], v[q], ss);
     }
-    float total_norm = sqrtf(block_sum<NT>(ss, red));
-    float coef = 1.0f;
-    if (clip_grad_norm > 0.0f) coef = fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f);
+    const float total_norm = sqrtf(block_sum<NT>(ss, red));
+    return clip_grad_norm > 0.0f ? fminf(clip_grad_norm / (total_norm + 1e-6f), 1.0f) : 1.0f;
+}
+
+template <int NT, bool GSMEM = false, bool FAST = false>
+DEV void apply_net(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
+                   float clip_grad_norm, float* red, int part = 0, int nparts = 1) {
+    const float coef = clip_coef<NT, GSMEM>(g, numel, clip_grad_norm, red);
     const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps, inv_bc2 = 1.0f / as.bc2_sqrt;
     const int n_tensors = 2 * net.num_linear + (net.action_std_log ? 1 : 0);
     const int first = part * NT + threadIdx.x, stride = nparts * NT;

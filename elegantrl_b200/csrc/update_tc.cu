@@ -49,6 +49,12 @@ static_assert(kOffGA % 1024 == 0 && kOffGB % 1024 == 0 && kOffWB % 1024 == 0, "M
 
 // ---- tensor memory columns
 constexpr uint32_t cZ1 = 0, cPhi = 64, cPlo = 128, cZ2 = 192, cG2 = 256, cG1 = 320;
+// Persistent launch: the net's parameters and Adam moments stay RESIDENT in tensor memory between the minibatches (the 176
+// columns behind the accumulators).  Thread (row, hf) owns W2 items 4 (tid + 256 q) + e (q, e < 4) and the small-tensor items
+// tid + 256 q (q < 6; index space W0 | b0 | b1 | W3 | b3 | action_std_log); TMEM lane = row, columns
+// cOpt + 48 kind + 24 hf + [0, 16) (W2) / + [16, 22) (small), kind = 0 parameter, 1 exp_avg, 2 exp_avg_sq.
+constexpr uint32_t cOpt = 336, kOptKind = 48, kOptHalf = 24, kOptSmall = 16;
+static_assert(cOpt + 3 * kOptKind <= 512, "tensor memory columns");
 
 // ---- peer-memory exchange (env-sharded update): system-scope release / acquire flags, relaxed system-scope data loads
 DEV void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -187,13 +193,132 @@ __device__ __noinline__ void px_reduce(const b200rl_peer_exchange& px, int px_of
 }
 
 // clip + Adam of one net, out of line for the same reason (its batched loads use 64 + registers of their own)
-__device__ __noinline__ void apply_from_smem(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
-                                             float clip_grad_norm, float* red) {
-    apply_net<kNT, true, true>(net, opt, as, g, numel, clip_grad_norm, red);
-}
 __device__ __noinline__ void apply_from_global(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
                                                float clip_grad_norm, float* red) {
     apply_net<kNT, false, true>(net, opt, as, g, numel, clip_grad_norm, red);
+}
+
+// ---- resident optimizer state (persistent launch)
+struct SmallItem { float* p; float* m; float* v; int g, sm, gz; };   // global pointers; flat-gradient, `small` and accumulator offsets
+DEV bool small_item(const b200rl_net& net, const b200rl_adam& opt, int idx, int S, int OUT, bool gaussian, SmallItem& it) {
+    const int nW0 = kHid * S, nW3 = OUT * kHid;
+    const int oB0 = nW0, oW1 = oB0 + kHid, oB1 = oW1 + kHid * kHid, oW2 = oB1 + kHid, oB2 = oW2 + nW3, oStd = oB2 + OUT;
+    it.gz = -1;
+    if (idx < nW0) { it.p = net.weight[0] + idx; it.m = opt.exp_avg_w[0] + idx; it.v = opt.exp_avg_sq_w[0] + idx; it.g = idx; it.sm = kSmW0 + idx; return true; }
+    if ((idx -= nW0) < kHid) { it.p = net.bias[0] + idx; it.m = opt.exp_avg_b[0] + idx; it.v = opt.exp_avg_sq_b[0] + idx; it.g = oB0 + idx; it.sm = kSmB0 + idx; return true; }
+    if ((idx -= kHid) < kHid) { it.p = net.bias[1] + idx; it.m = opt.exp_avg_b[1] + idx; it.v = opt.exp_avg_sq_b[1] + idx; it.g = oB1 + idx; it.sm = kSmB2 + idx; it.gz = kSmGB2 + idx; return true; }
+    if ((idx -= kHid) < nW3) { it.p = net.weight[2] + idx; it.m = opt.exp_avg_w[2] + idx; it.v = opt.exp_avg_sq_w[2] + idx; it.g = oW2 + idx; it.sm = kSmW3 + idx; it.gz = kSmGW3 + idx; return true; }
+    if ((idx -= nW3) < OUT) { it.p = net.bias[2] + idx; it.m = opt.exp_avg_b[2] + idx; it.v = opt.exp_avg_sq_b[2] + idx; it.g = oB2 + idx; it.sm = kSmB3 + idx; it.gz = kSmGB3 + idx; return true; }
+    if (gaussian && (idx -= OUT) < OUT) { it.p = net.action_std_log + idx; it.m = opt.exp_avg_std + idx; it.v = opt.exp_avg_sq_std + idx; it.g = oStd + idx; it.sm = kSmStd + idx; it.gz = kSmGStd + idx; return true; }
+    return false;
+}
+// parameters + moments: global -> tensor memory, once per launch
+__device__ __noinline__ void opt_load(const b200rl_net& net, const b200rl_adam& opt, uint32_t tl, int tid, int S, int OUT, bool gaussian) {
+    const uint32_t base = tl + cOpt + (uint32_t)(tid >> 7) * kOptHalf;
+    const float* w2[3] = {net.weight[1], opt.exp_avg_w[1], opt.exp_avg_sq_w[1]};
+#pragma unroll
+    for (int kind = 0; kind < 3; ++kind) {
+        uint32_t r[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 w = __ldcg(reinterpret_cast<const float4*>(w2[kind]) + tid + kNT * q);
+            r[4 * q] = __float_as_uint(w.x); r[4 * q + 1] = __float_as_uint(w.y); r[4 * q + 2] = __float_as_uint(w.z); r[4 * q + 3] = __float_as_uint(w.w);
+        }
+        tc05::tmem_st_32x32b_x16(base + kind * kOptKind, r);
+        uint32_t sr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            SmallItem it;
+            sr[q] = 0u;
+            if (q < 6 && small_item(net, opt, tid + kNT * q, S, OUT, gaussian, it))
+                sr[q] = __float_as_uint(__ldcg(kind == 0 ? it.p : (kind == 1 ? it.m : it.v)));
+        }
+        tc05::tmem_st_32x32b_x8(base + kind * kOptKind + kOptSmall, sr);
+    }
+    tc05::tmem_st_wait();
+}
+// clip_grad_norm_ + Adam.step on the resident state, and the next minibatch's operand images straight from the registers that
+// hold the new parameters: no global round trip per minibatch (the L2 latencies of p / m / v loads, their stores and the
+// re-read by the staging were 30 k of the 78 k cycles of a minibatch, profiles/r02_v8_update_tc_phases.log).  `last`: write
+// everything back to the caller's tensors.
+__device__ __noinline__ void opt_apply_resident(const b200rl_net& net, const b200rl_adam& opt, const AdamScalars& as, const float* g, int numel,
+                                                float clip_grad_norm, float* red, float* small, uint32_t w2_hi, uint32_t w2_lo, uint32_t wb_hi,
+                                                uint32_t wb_lo, uint32_t tl, int tid, int S, int OUT, bool gaussian, bool last) {
+    const float coef = clip_coef<kNT, true>(g, numel, clip_grad_norm, red);
+    const float b1 = opt.beta1, b2 = opt.beta2, eps = opt.eps, inv_bc2 = 1.0f / as.bc2_sqrt;
+    const uint32_t base = tl + cOpt + (uint32_t)(tid >> 7) * kOptHalf;
+    const int oW1 = kHid * S + kHid;
+    {   // ---- W2
+        float p[16], m[16], v[16];
+        tc05::tmem_ld_32x32b_x16(base, p);
+        tc05::tmem_ld_32x32b_x16(base + kOptKind, m);
+        tc05::tmem_ld_32x32b_x16(base + 2 * kOptKind, v);
+        tc05::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 gg = *reinterpret_cast<const float4*>(g + oW1 + 4 * (tid + kNT * q));
+            adam_step<true>(p[4 * q], m[4 * q], v[4 * q], gg.x * coef, b1, b2, eps, as, inv_bc2);
+            adam_step<true>(p[4 * q + 1], m[4 * q + 1], v[4 * q + 1], gg.y * coef, b1, b2, eps, as, inv_bc2);
+            adam_step<true>(p[4 * q + 2], m[4 * q + 2], v[4 * q + 2], gg.z * coef, b1, b2, eps, as, inv_bc2);
+            adam_step<true>(p[4 * q + 3], m[4 * q + 3], v[4 * q + 3], gg.w * coef, b1, b2, eps, as, inv_bc2);
+        }
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(p[i]);
+        tc05::tmem_st_32x32b_x16(base, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(m[i]);
+        tc05::tmem_st_32x32b_x16(base + kOptKind, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+        tc05::tmem_st_32x32b_x16(base + 2 * kOptKind, r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // forward (K-major) and backward (MN-major) images of the new W2, hi / lo planes
+            const int i = 4 * (tid + kNT * q), n = i >> 6, k = i & 63;
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { h[e] = tc05::tf32_hi(p[4 * q + e]); l[e] = p[4 * q + e] - h[e]; }
+            const uint32_t offf = tc05::operand_offset(n, k, kHid);
+            st_shared_v4(w2_hi + offf, h[0], h[1], h[2], h[3]);
+            st_shared_v4(w2_lo + offf, l[0], l[1], l[2], l[3]);
+            const uint32_t offb = mn_swizzle((uint32_t)(k >> 5) * kWbLBO + (uint32_t)(n >> 2) * kMnSBO + (uint32_t)(n & 3) * 128 + (uint32_t)(k & 31) * 4);
+            st_shared_v4(wb_hi + offb, h[0], h[1], h[2], h[3]);
+            st_shared_v4(wb_lo + offb, l[0], l[1], l[2], l[3]);
+            if (last) {
+                reinterpret_cast<float4*>(net.weight[1])[tid + kNT * q] = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+                reinterpret_cast<float4*>(opt.exp_avg_w[1])[tid + kNT * q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+                reinterpret_cast<float4*>(opt.exp_avg_sq_w[1])[tid + kNT * q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+        }
+    }
+    {   // ---- the small tensors
+        float p[8], m[8], v[8];
+        tc05::tmem_ld_32x32b_x8(base + kOptSmall, p);
+        tc05::tmem_ld_32x32b_x8(base + kOptKind + kOptSmall, m);
+        tc05::tmem_ld_32x32b_x8(base + 2 * kOptKind + kOptSmall, v);
+        tc05::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            SmallItem it;
+            if (small_item(net, opt, tid + kNT * q, S, OUT, gaussian, it)) {
+                adam_step<true>(p[q], m[q], v[q], g[it.g] * coef, b1, b2, eps, as, inv_bc2);
+                small[it.sm] = p[q];
+                if (it.gz >= 0) small[it.gz] = 0.0f;   // the head's gradient accumulators of the next minibatch
+                if (last) { *it.p = p[q]; *it.m = m[q]; *it.v = v[q]; }
+            }
+        }
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(p[i]);
+        tc05::tmem_st_32x32b_x8(base + kOptSmall, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(m[i]);
+        tc05::tmem_st_32x32b_x8(base + kOptKind + kOptSmall, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+        tc05::tmem_st_32x32b_x8(base + 2 * kOptKind + kOptSmall, r);
+    }
+    tc05::tmem_st_wait();
 }
 
 #define TC_MARK(i) do { if (A.profile && ni == 0 && tid == 0 && u == U - 1) reinterpret_cast<long long*>(A.hdr)[8 + (i)] = clock64(); } while (0)
@@ -249,6 +374,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
     const uint32_t ga_addr = tc05::smem_u32(smem + kOffGA), gb_addr = tc05::smem_u32(smem + kOffGB);
     uint32_t phase = 0;
     double acc_c = 0.0, acc_s = 0.0, acc_e = 0.0;   // thread 0: loss sums over the minibatches (persistent mode)
+    if (persistent) opt_load(net, A.opt[ni], tl, tid, S, OUT, gaussian);
 
     // advantage normalisation (reference :149): from the caller's statistics, or -- env-sharded -- reduced here over the shards
     __shared__ float s_stats[2];
@@ -341,7 +467,8 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
             if (packed) sampled = ids_u ? ids_u[slot] : (int64_t)draw * A.local_batch + slot;
             else sampled = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
         }
-        stage_params(net, small, w2_hi, w2_lo, wb_hi, wb_lo, tid, S, OUT, gaussian);
+        // (persistent launch: minibatch u > 0 finds the images of its parameters written by the previous minibatch's Adam step)
+        if (!persistent || u == 0) stage_params(net, small, w2_hi, w2_lo, wb_hi, wb_lo, tid, S, OUT, gaussian);
 
         // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n)
         float um = 0.f, lp_old = 0.f, adv = 0.f, rs = 0.f;
@@ -801,7 +928,8 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
                 }
             }
             __syncthreads();
-            apply_from_smem(net, A.opt[ni], s_adam, g_smem, numel, A.hp.clip_grad_norm, red);
+            opt_apply_resident(net, A.opt[ni], s_adam, g_smem, numel, A.hp.clip_grad_norm, red, small, w2_hi, w2_lo, wb_hi, wb_lo, tl, tid,
+                               S, OUT, gaussian, u == U - 1);
             __syncthreads();
             TC_MARK(10);
         } else if (A.fused_apply) {
