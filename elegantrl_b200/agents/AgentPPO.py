@@ -125,6 +125,8 @@ class AgentPPO:
         self._lib_handle = None      # ctypes handle (not pickled: see __getstate__)
         self._fused_pre = None       # ((n, h), output tensors) allocated ahead for the next fused rollout
         self._rollout_args = None    # reused b200rl_rollout_args block
+        self._rollout_args_key = None
+        self._rollout_args_keep = None
         self._desc_cache = {}        # id(module) -> (parameter pointers, descriptor)
         self._dist_group = None      # set by enable_data_parallel()
         self._px = None
@@ -141,7 +143,7 @@ class AgentPPO:
     def __getstate__(self):
         """The agent may be pickled (multiprocessing): raw handles, pointer blocks and CUDA graphs are per process."""
         state = dict(self.__dict__)
-        state.update(_lib_handle=None, _fused_pre=None, _rollout_args=None, _desc_cache={}, _rollout_graphs={},
+        state.update(_lib_handle=None, _fused_pre=None, _rollout_args=None, _rollout_args_key=None, _rollout_args_keep=None, _desc_cache={}, _rollout_graphs={},
                      _workspace=None, _value_cache=None, _px=None, _dist_group=None, _host_result=None)
         return state
 
@@ -158,14 +160,22 @@ class AgentPPO:
 
     def _net_desc(self, module: nn.Module) -> _lib.Net:
         """C descriptor aliasing the module's parameter storages; cached per module and revalidated on every call by the
-        storages' addresses (``load_state_dict`` keeps them, ``.to()`` / re-assignment does not), the activation name and the
-        presence of the normalisation statistics."""
-        ptrs = tuple(p.data_ptr() for p in module.parameters()) + tuple(b.data_ptr() for b in module.buffers())
+        storages' addresses (``load_state_dict`` keeps them, ``.to()`` does not; replacing the module rebuilds it, replacing a
+        LAYER of a live module after the first call is not supported -- the reference never does)."""
         hit = self._desc_cache.get(id(module))
-        if hit is not None and hit[0] == ptrs and hit[2] is module:
-            return hit[1]
+        if hit is not None and hit[2] is module:
+            # fast path (this sits between a host synchronisation and the rollout launch): the Parameter / buffer OBJECTS seen
+            # when the descriptor was built are kept alive here, so comparing their current addresses needs no module traversal
+            ptrs, net, _, tensors = hit
+            for t, p in zip(tensors, ptrs):
+                if t.data_ptr() != p:
+                    break
+            else:
+                return net
+        tensors = tuple(module.parameters()) + tuple(module.buffers())
+        ptrs = tuple(t.data_ptr() for t in tensors)
         net = self._build_net_desc(module)
-        self._desc_cache[id(module)] = (ptrs, net, module)
+        self._desc_cache[id(module)] = (ptrs, net, module, tensors)
         return net
 
     def _build_net_desc(self, module: nn.Module) -> _lib.Net:
@@ -340,9 +350,16 @@ class AgentPPO:
         args = self._rollout_args
         if args is None:
             args = self._rollout_args = _lib.RolloutArgs()
-        args.actor, args.critic = C.pointer(act_desc), C.pointer(cri_desc)
-        args.num_envs, args.horizon_len, args.max_step, args.reward_scale = n, h, env.max_step, float(self.reward_scale)
-        args.theta, args.theta_dot, args.cur_step = theta.data_ptr(), theta_dot.data_ptr(), cur_step.data_ptr()
+            self._rollout_args_key = None
+        # the fields that do not change from cycle to cycle are written once per (env, nets, shape)
+        key = (id(env), id(act_desc), id(cri_desc), n, h, env.max_step, id(theta), id(theta_dot), id(cur_step))
+        if self._rollout_args_key != key:
+            args.actor, args.critic = C.pointer(act_desc), C.pointer(cri_desc)
+            args.num_envs, args.horizon_len, args.max_step = n, h, env.max_step
+            args.theta, args.theta_dot, args.cur_step = theta.data_ptr(), theta_dot.data_ptr(), cur_step.data_ptr()
+            self._rollout_args_key = key
+            self._rollout_args_keep = (env, act_desc, cri_desc, theta, theta_dot, cur_step)   # ids above stay unique while these live
+        args.reward_scale = float(self.reward_scale)
         args.states, args.actions, args.logprobs, args.rewards = states.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), rewards.data_ptr()
         args.undones, args.unmasks, args.values = undones.data_ptr(), unmasks.data_ptr(), values.data_ptr()
         args.last_state, args.last_value = last_state.data_ptr(), last_value.data_ptr()

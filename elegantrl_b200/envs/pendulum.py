@@ -54,7 +54,8 @@ class PendulumVecEnv:
         self.generator.manual_seed(self.seed)
         # ONE [3, N] block (theta, theta_dot, cur_step as int32 bits): a host loop moves the whole env state with a single copy
         self._block = th.zeros((3, self.num_envs), dtype=th.float32, device=self.device)
-        self.theta, self.theta_dot, self.cur_step = self._block[0], self._block[1], self._block[2].view(th.int32)
+        self._rows = (self._block[0], self._block[1], self._block[2].view(th.int32))
+        self.theta, self.theta_dot, self.cur_step = self._rows
         self.global_step = 0  # counts step() calls + fused steps: Philox offset of the fused kernel
         self.reset_noise: Optional[TEN] = None  # injected U[0,1) noise [T, N, 2] for parity tests
         self._reset_noise_row = 0
@@ -114,16 +115,19 @@ class PendulumVecEnv:
     def engine_state(self) -> Tuple[TEN, TEN, TEN]:
         """Tensors the fused rollout kernel updates in place: rows of the [3, N] state block.  ``step`` / a caller may have
         rebound the attributes to fresh tensors; those are copied back into the block first."""
-        blk = self._block
-        if self.theta.data_ptr() != blk.data_ptr():
-            blk[0].copy_(self.theta)
-            self.theta = blk[0]
-        if self.theta_dot.data_ptr() != blk[1].data_ptr():
-            blk[1].copy_(self.theta_dot)
-            self.theta_dot = blk[1]
-        if self.cur_step.data_ptr() != blk[2].data_ptr():
-            blk[2].view(th.int32).copy_(self.cur_step)
-            self.cur_step = blk[2].view(th.int32)
+        rows = self._rows   # the block's row views, created once: an identity test per call instead of three indexing ops
+        if rows is None:
+            blk = self._block
+            rows = self._rows = (blk[0], blk[1], blk[2].view(th.int32))
+        if self.theta is not rows[0]:
+            rows[0].copy_(self.theta)
+            self.theta = rows[0]
+        if self.theta_dot is not rows[1]:
+            rows[1].copy_(self.theta_dot)
+            self.theta_dot = rows[1]
+        if self.cur_step is not rows[2]:
+            rows[2].copy_(self.cur_step)
+            self.cur_step = rows[2]
         return self.theta, self.theta_dot, self.cur_step
 
     def engine_state_block(self) -> TEN:
