@@ -386,19 +386,11 @@ int b200rl_launch_rollout_ts(const RolloutParams& P_in, cudaStream_t stream) {
     RolloutParams P = P_in;
     P.rows_per_cta = rows_per_cta_for(P.N);
     const char* v = getenv("B200RL_TS_VARIANT");
+    // built: the default, its baseline and the actor-only experiment; the other scheduling variants measured in
+    // profiles/r02_v3_rollout_ts_variants.log (bits 1, 4, 8) are template parameters away
     switch (v ? atoi(v) : kDefaultVariant) {
         case 0: return launch_variant<0>(P, stream);
-        case 1: return launch_variant<1>(P, stream);
         case 2: return launch_variant<2>(P, stream);
-        case 3: return launch_variant<3>(P, stream);
-        case 4: return launch_variant<4>(P, stream);
-        case 5: return launch_variant<5>(P, stream);
-        case 7: return launch_variant<7>(P, stream);
-        case 8: return launch_variant<8>(P, stream);
-        case 9: return launch_variant<9>(P, stream);
-        case 11: return launch_variant<11>(P, stream);
-        case 13: return launch_variant<13>(P, stream);
-        case 15: return launch_variant<15>(P, stream);
         case 18: return launch_variant<18>(P, stream);
         default: break;
     }

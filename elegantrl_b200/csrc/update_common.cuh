@@ -96,6 +96,22 @@ DEV float ld_grad(const float* p) { return GSMEM ? *p : __ldcg(p); }
 template <bool GSMEM>
 DEV float4 ld_grad4(const float4* p) { return GSMEM ? *p : __ldcg(p); }
 
+// three sums at the price of one (same per-value arithmetic as block_sum: warp shuffle tree, then the warps in order)
+template <int NT>
+DEV void block_sum3(float& a, float& b, float& c, float* red /*[32]*/) {
+    static_assert(3 * (NT / 32) <= 32, "red[] holds three partial sums per warp");
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        red[w] = a; red[NT / 32 + w] = b; red[2 * (NT / 32) + w] = c;
+    }
+    __syncthreads();
+    a = b = c = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { a += red[w]; b += red[NT / 32 + w]; c += red[2 * (NT / 32) + w]; }
+}
+
 // clip_grad_norm_'s scale factor for one net's gradient (the whole CTA takes part)
 template <int NT, bool GSMEM>
 DEV float clip_coef(const float* g, int numel, float clip_grad_norm, float* red) {

@@ -891,7 +891,8 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
 
         // ------------------------------------------------------------ loss sums
         {
-            const float c = block_sum<kNT>(loss_c, red), s = block_sum<kNT>(loss_s, red), e = block_sum<kNT>(loss_e, red);
+            float c = loss_c, s = loss_s, e = loss_e;
+            block_sum3<kNT>(c, s, e, red);
             if (tid == 0) {
                 if (sharded) { g[numel] = c * inv_bsz; g[numel + 1] = s * inv_bsz; g[numel + 2] = e * inv_bsz; }
                 else if (persistent) { acc_c += (double)(c * inv_bsz); acc_s += (double)(s * inv_bsz); acc_e += (double)(e * inv_bsz); }
