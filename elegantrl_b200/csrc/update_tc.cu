@@ -444,6 +444,69 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
     const int px_off0 = kPxStatFloats + (ni ? px_segment(A.grad_numel[0]) : 0);
     const int px_parity_stride = px_segment(A.grad_numel[0]) + px_segment(A.grad_numel[1]);
 
+    // one sampled transition of minibatch uu for this thread's slot (both threads of a sample load it)
+    auto load_record = [&](int uu, float& um, float& lp_old, float& adv, float& rs, float (&act)[OUTC], float (&x)[SC]) {
+        um = 0.f; lp_old = 0.f; adv = 0.f; rs = 0.f;
+#pragma unroll
+        for (int a = 0; a < OUTC; ++a) act[a] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < SC; ++k) x[k] = 0.0f;
+        const int slot = blockIdx.x * kT + row;
+        if (slot >= A.local_batch) return;
+        const int Adim = discrete ? 1 : A.net[0].dims[3];
+        if (gathered) {   // sample `slot` of the global minibatch = record (uu, slot % lb) of rank slot / lb
+            const float* recp = A.px.data[slot / lb] + px_rec_off + (size_t)(uu * lb + slot % lb) * rec;
+            const float4 tail = ld_relaxed_sys_v4(recp + rec_tail);
+            um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
+#pragma unroll
+            for (int k = 0; k < SC; ++k) if (k < S) x[k] = ld_relaxed_sys(recp + k);
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = ld_relaxed_sys(recp + rec_act + a);
+            return;
+        }
+        const int64_t* ids_u = A.ids ? A.ids + (persistent ? (size_t)uu * A.local_batch : 0) : nullptr;
+        const uint64_t draw = A.draw + (uint64_t)uu;
+        if (packed) {
+            const int64_t sampled = ids_u ? ids_u[slot] : (int64_t)draw * A.local_batch + slot;
+            const float* recp = A.buf.states + sampled * rec;
+            const float4 tail = *reinterpret_cast<const float4*>(recp + rec_tail);
+            um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
+#pragma unroll
+            for (int k = 0; k < SC; ++k) if (k < S) x[k] = recp[k];
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = recp[rec_act + a];
+            return;
+        }
+        const uint64_t range = (uint64_t)H * (uint64_t)N;
+        const int64_t sampled = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, range);
+        int64_t tn;
+        if (range <= 0xFFFFFFFFull) {   // 32-bit division: the 64-bit one is a ~150-instruction dependent chain in front of the loads
+            const uint32_t s32 = (uint32_t)sampled, q = s32 / (uint32_t)H;
+            tn = (int64_t)(s32 - q * (uint32_t)H) * N + q;
+        } else {
+            tn = (sampled % H) * N + sampled / H;
+        }
+        um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
+        lp_old = A.buf.logprobs[tn];
+        adv = A.buf.advantages[tn];
+        if (normalise) adv = (adv - s_stats[0]) / (s_stats[1] + 1e-5f);
+        rs = A.buf.reward_sums[tn];
+#pragma unroll
+        for (int k = 0; k < SC; ++k) if (k < S) x[k] = A.buf.states[tn * S + k];
+        if (discrete) act[0] = (float)reinterpret_cast<const int32_t*>(A.buf.actions)[tn];
+        else {
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = A.buf.actions[tn * Adim + a];
+        }
+    };
+    float n_um = 0.f, n_lp = 0.f, n_adv = 0.f, n_rs = 0.f;   // the prefetched record of the next minibatch
+    float n_act[OUTC];
+    float n_x[SC];
+#pragma unroll
+    for (int a = 0; a < OUTC; ++a) n_act[a] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < SC; ++k) n_x[k] = 0.0f;
+
     for (int u = 0; u < U; ++u) {
         // env-sharded: this minibatch's gradient goes to the own exchange buffer (two alternate so that a rank that is one
         // minibatch ahead never overwrites what a peer still reads); the reduced gradient lands in the workspace as usual
@@ -457,62 +520,24 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
         // ------------------------------------------------------------ parameters -> operand images (Adam rewrote them)
         // every load of the minibatch's parameters is issued before anything is stored: ONE L2 latency, not one per element
         TC_MARK(0);
-        // the sampled index first: its (dependent) load chain overlaps the parameter staging below
-        const int64_t* ids_u = A.ids ? A.ids + (persistent ? (size_t)u * A.local_batch : 0) : nullptr;
-        const uint64_t draw = A.draw + (uint64_t)u;
         const int slot = tile * kT + row;   // both threads of a sample gather its scalars (the loss is evaluated redundantly)
         const bool valid = slot < A.local_batch;
-        int64_t sampled = 0;
-        if (valid && !gathered) {
-            if (packed) sampled = ids_u ? ids_u[slot] : (int64_t)draw * A.local_batch + slot;
-            else sampled = ids_u ? ids_u[slot] : sample_index(A.seed, draw, (uint32_t)slot, (uint64_t)H * (uint64_t)N);
+        // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n).  Persistent
+        // launch: the record of minibatch u > 0 was requested during the backward pass of minibatch u - 1 (the indices do not depend
+        // on the parameters), so its HBM / NVLink latency and the index arithmetic are off the critical path
+        float um, lp_old, adv, rs;
+        float act[OUTC];
+        float x[SC];
+        if (u == 0) load_record(0, um, lp_old, adv, rs, act, x);
+        else {
+            um = n_um; lp_old = n_lp; adv = n_adv; rs = n_rs;
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) act[a] = n_act[a];
+#pragma unroll
+            for (int k = 0; k < SC; ++k) x[k] = n_x[k];
         }
         // (persistent launch: minibatch u > 0 finds the images of its parameters written by the previous minibatch's Adam step)
         if (!persistent || u == 0) stage_params(net, small, w2_hi, w2_lo, wb_hi, wb_lo, tid, S, OUT, gaussian);
-
-        // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n)
-        float um = 0.f, lp_old = 0.f, adv = 0.f, rs = 0.f;
-        float act[OUTC];
-        float x[SC];
-#pragma unroll
-        for (int a = 0; a < OUTC; ++a) act[a] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < SC; ++k) x[k] = 0.0f;
-        if (valid && gathered) {   // sample `slot` of the global minibatch = record (u, slot % lb) of rank slot / lb
-            const int Adim = discrete ? 1 : A.net[0].dims[3];
-            const float* recp = A.px.data[slot / lb] + px_rec_off + (size_t)(u * lb + slot % lb) * rec;
-            const float4 tail = ld_relaxed_sys_v4(recp + rec_tail);
-            um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
-#pragma unroll
-            for (int k = 0; k < SC; ++k) if (k < S) x[k] = ld_relaxed_sys(recp + k);
-#pragma unroll
-            for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = ld_relaxed_sys(recp + rec_act + a);
-        } else if (valid) {
-            const int Adim = discrete ? 1 : A.net[0].dims[3];
-            if (packed) {
-                const float* recp = A.buf.states + sampled * rec;
-                const float4 tail = *reinterpret_cast<const float4*>(recp + rec_tail);
-                um = tail.x; lp_old = tail.y; adv = tail.z; rs = tail.w;
-#pragma unroll
-                for (int k = 0; k < SC; ++k) if (k < S) x[k] = recp[k];
-#pragma unroll
-                for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = recp[rec_act + a];
-            } else {
-                const int64_t tn = (sampled % H) * N + sampled / H;
-                um = A.buf.unmasks[tn] ? 1.0f : 0.0f;
-                lp_old = A.buf.logprobs[tn];
-                adv = A.buf.advantages[tn];
-                if (normalise) adv = (adv - s_stats[0]) / (s_stats[1] + 1e-5f);
-                rs = A.buf.reward_sums[tn];
-#pragma unroll
-                for (int k = 0; k < SC; ++k) if (k < S) x[k] = A.buf.states[tn * S + k];
-                if (discrete) act[0] = (float)reinterpret_cast<const int32_t*>(A.buf.actions)[tn];
-                else {
-#pragma unroll
-                    for (int a = 0; a < OUTC; ++a) if (a < Adim) act[a] = A.buf.actions[tn * Adim + a];
-                }
-            }
-        }
         __syncthreads();   // staged small parameters (state_norm statistics, W0 / b0) are visible
         for (int i = tid; i < kHid * K1; i += kNT) {   // layer-1 B planes from the staged W0 / b0
             const int n = i / K1, k = i - n * K1;
@@ -721,6 +746,8 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
         }
 
         TC_MARK(5);
+        // the scalars of this minibatch's record are dead from here on: request the next one (consumed at the top of the loop)
+        if (u + 1 < U) load_record(u + 1, n_um, n_lp, n_adv, n_rs, n_act, n_x);
         // ------------------------------------------------------------ dZ2 = (dOut W3) * GELU'(Z2): TMEM planes + rows; dW3 by shuffles
         if (hf != 0) { loss_c = 0.0f; loss_s = 0.0f; loss_e = 0.0f; }   // the loss sums count every sample once
 #pragma unroll 1
