@@ -174,15 +174,17 @@ DEV void issue_linear_ts_backward(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t 
     }
 }
 // D[64 x N] = G^T * Q over the 128 samples: G [128][64] and Q [128][N <= 32] as row-written hi / lo images (lo plane = hi
-// plane address + plane bytes).  48 UMMAs 64 x N x 8; accumulator rows at TMEM lanes (m % 16) + 32 * (m / 16).
-DEV void issue_weight_grad(uint32_t tmem_d, uint32_t ga, uint32_t ga_plane_bytes, uint32_t gb, uint32_t gb_plane_bytes, int N) {
+// plane address + plane bytes).  48 UMMAs 64 x N x 8; accumulator rows at TMEM lanes (m % 16) + 32 * (m / 16).  `accumulate`:
+// add to what the accumulator holds (a CTA walking several tiles of a minibatch).
+DEV void issue_weight_grad(uint32_t tmem_d, uint32_t ga, uint32_t ga_plane_bytes, uint32_t gb, uint32_t gb_plane_bytes, int N,
+                           bool accumulate = false) {
     const uint32_t idesc = tc05::make_idesc_tf32_ex(64, N, true, true);
     const uint64_t a_hi0 = make_mn_desc(ga, kRowLBO), a_lo0 = make_mn_desc(ga + ga_plane_bytes, kRowLBO);
     const uint64_t b_hi0 = make_mn_desc(gb, kRowLBO), b_lo0 = make_mn_desc(gb + gb_plane_bytes, kRowLBO);
 #pragma unroll
     for (int ks = 0; ks < kTile / 8; ++ks) {
         const uint64_t o = (uint64_t)(ks * ((2 * kMnSBO) >> 4));
-        tc05::mma_tf32(tmem_d, a_hi0 + o, b_hi0 + o, idesc, ks > 0);
+        tc05::mma_tf32(tmem_d, a_hi0 + o, b_hi0 + o, idesc, ks > 0 || accumulate);
         tc05::mma_tf32(tmem_d, a_lo0 + o, b_hi0 + o, idesc, true);
         tc05::mma_tf32(tmem_d, a_hi0 + o, b_lo0 + o, idesc, true);
     }

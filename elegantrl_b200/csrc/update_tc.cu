@@ -29,6 +29,7 @@ constexpr int kT = 128;    // samples per tile = TMEM lanes
 constexpr int kNT = 256;   // threads: TWO per sample (warp w and w + 4 share a lane quarter and split the 64 columns)
 constexpr int kMaxS = 11, kMaxOut = 8, kK1Max = 24;
 constexpr int kAdamTab = 64;
+constexpr int kMaxCtasPerNet = 74;   // 148 SMs / 2 nets
 
 // ---- dynamic shared memory map (bytes)
 constexpr int kOffW2 = 0;                                      // W2 hi / lo K-major images (forward)
@@ -42,7 +43,8 @@ constexpr int kOffB1 = kOffA1 + kA1Bytes;                      // layer-1 B plan
 constexpr int kOffSmall = kOffB1 + 2 * kB1PlaneBytes;
 constexpr int kSmW3 = 0, kSmB3 = 512, kSmStd = 520, kSmAvg = 528, kSmSd = 544, kSmGW3 = 560, kSmGB3 = 1072, kSmGStd = 1080,
               kSmB2 = 1088, kSmGB2 = 1152, kSmW0 = 1216, kSmB0 = 1216 + 64 * kMaxS, kSmallFloats = kSmB0 + 64;
-constexpr int kOffBar = kOffSmall + kSmallFloats * 4;
+constexpr int kOffPart = kOffSmall + kSmallFloats * 4;   // head partial sums of the two column halves: [2][128][OUTC <= 8]
+constexpr int kOffBar = kOffPart + 2 * kT * kMaxOut * 4;
 constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kSmemBytes <= 226 * 1024, "shared memory budget");
 static_assert(kOffGA % 1024 == 0 && kOffGB % 1024 == 0 && kOffWB % 1024 == 0, "MN-major images: swizzle-atom alignment");
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kT - 1), hf = tid >> 7, quarter = warp & 3;   // sample row, column half, TMEM lane quarter
     const int ni = blockIdx.y, tile = blockIdx.x;
+    const int n_tiles = (A.local_batch + kT - 1) / kT;   // tiles of one minibatch (persistent launch: 1)
     const b200rl_net& net = A.net[ni];
     const int S = net.dims[0], OUT = net.dims[3];
     const int K1 = (2 * S + 1 + 7) & ~7, N1 = (S + 1 + 7) & ~7;
@@ -445,13 +448,13 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
     const int px_parity_stride = px_segment(A.grad_numel[0]) + px_segment(A.grad_numel[1]);
 
     // one sampled transition of minibatch uu for this thread's slot (both threads of a sample load it)
-    auto load_record = [&](int uu, float& um, float& lp_old, float& adv, float& rs, float (&act)[OUTC], float (&x)[SC]) {
+    auto load_record = [&](int uu, int tt, float& um, float& lp_old, float& adv, float& rs, float (&act)[OUTC], float (&x)[SC]) {
         um = 0.f; lp_old = 0.f; adv = 0.f; rs = 0.f;
 #pragma unroll
         for (int a = 0; a < OUTC; ++a) act[a] = 0.0f;
 #pragma unroll
         for (int k = 0; k < SC; ++k) x[k] = 0.0f;
-        const int slot = blockIdx.x * kT + row;
+        const int slot = tt * kT + row;
         if (slot >= A.local_batch) return;
         const int Adim = discrete ? 1 : A.net[0].dims[3];
         if (gathered) {   // sample `slot` of the global minibatch = record (uu, slot % lb) of rank slot / lb
@@ -520,22 +523,6 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
         // ------------------------------------------------------------ parameters -> operand images (Adam rewrote them)
         // every load of the minibatch's parameters is issued before anything is stored: ONE L2 latency, not one per element
         TC_MARK(0);
-        const int slot = tile * kT + row;   // both threads of a sample gather its scalars (the loss is evaluated redundantly)
-        const bool valid = slot < A.local_batch;
-        // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n).  Persistent
-        // launch: the record of minibatch u > 0 was requested during the backward pass of minibatch u - 1 (the indices do not depend
-        // on the parameters), so its HBM / NVLink latency and the index arithmetic are off the critical path
-        float um, lp_old, adv, rs;
-        float act[OUTC];
-        float x[SC];
-        if (u == 0) load_record(0, um, lp_old, adv, rs, act, x);
-        else {
-            um = n_um; lp_old = n_lp; adv = n_adv; rs = n_rs;
-#pragma unroll
-            for (int a = 0; a < OUTC; ++a) act[a] = n_act[a];
-#pragma unroll
-            for (int k = 0; k < SC; ++k) x[k] = n_x[k];
-        }
         // (persistent launch: minibatch u > 0 finds the images of its parameters written by the previous minibatch's Adam step)
         if (!persistent || u == 0) stage_params(net, small, w2_hi, w2_lo, wb_hi, wb_lo, tid, S, OUT, gaussian);
         __syncthreads();   // staged small parameters (state_norm statistics, W0 / b0) are visible
@@ -549,6 +536,29 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
             const uint32_t off = tc05::operand_offset(n, k, K1);
             *reinterpret_cast<float*>(smem + kOffB1 + off) = hi;                                            // [W_hi, b_hi, W_hi, 0]
             *reinterpret_cast<float*>(smem + kOffB1 + kB1PlaneBytes + off) = k <= S ? full - hi : 0.0f;     // [W_lo, b_lo, 0, 0]
+        }
+        // A minibatch of several tiles (one launch per minibatch): this CTA walks tiles tile0, tile0 + gridDim.x, ... with the
+        // operand images staged ONCE; the weight-gradient accumulators in tensor memory (and the head's in shared memory) keep
+        // accumulating over its tiles, so the flat gradient is added to the global buffer once per CTA, not once per tile.
+        float tot_c = 0.0f, tot_s = 0.0f, tot_e = 0.0f;
+        float x[SC];
+        bool valid = false;
+        for (int tt = tile; tt < n_tiles; tt += (int)gridDim.x) {
+        const bool first_tile = tt == tile;
+        const int slot = tt * kT + row;   // both threads of a sample gather its scalars (the loss is evaluated redundantly)
+        valid = slot < A.local_batch;
+        // ------------------------------------------------------------ gather (reference :178-187): ids -> (t, n).  The record of
+        // every tile / minibatch but the first was requested during the backward pass of the previous one (the indices do not
+        // depend on the parameters), so its HBM / NVLink latency and the index arithmetic are off the critical path
+        float um, lp_old, adv, rs;
+        float act[OUTC];
+        if (u == 0 && first_tile) load_record(0, tt, um, lp_old, adv, rs, act, x);
+        else {
+            um = n_um; lp_old = n_lp; adv = n_adv; rs = n_rs;
+#pragma unroll
+            for (int a = 0; a < OUTC; ++a) act[a] = n_act[a];
+#pragma unroll
+            for (int k = 0; k < SC; ++k) x[k] = n_x[k];
         }
         TC_MARK(1);
         if (valid && net.state_avg) {
@@ -631,9 +641,9 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
                 }
             }
         }
-        {   // the two halves of a row meet through shared memory (the layer-1 B planes are free once layer 1 is done); both
+        {   // the two halves of a row meet through shared memory; both
             // threads then hold the full head output and evaluate the loss redundantly (fixed order: half 0 + half 1 + bias)
-            float* part = reinterpret_cast<float*>(smem + kOffB1);
+            float* part = reinterpret_cast<float*>(smem + kOffPart);
 #pragma unroll
             for (int a = 0; a < OUTC; ++a) if (a < OUT) part[(hf * kT + row) * OUTC + a] = out[a];
             __syncthreads();
@@ -747,9 +757,10 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
 
         TC_MARK(5);
         // the scalars of this minibatch's record are dead from here on: request the next one (consumed at the top of the loop)
-        if (u + 1 < U) load_record(u + 1, n_um, n_lp, n_adv, n_rs, n_act, n_x);
+        if (tt + (int)gridDim.x < n_tiles) load_record(u, tt + (int)gridDim.x, n_um, n_lp, n_adv, n_rs, n_act, n_x);
+        else if (u + 1 < U) load_record(u + 1, tile, n_um, n_lp, n_adv, n_rs, n_act, n_x);
         // ------------------------------------------------------------ dZ2 = (dOut W3) * GELU'(Z2): TMEM planes + rows; dW3 by shuffles
-        if (hf != 0) { loss_c = 0.0f; loss_s = 0.0f; loss_e = 0.0f; }   // the loss sums count every sample once
+        if (hf == 0) { tot_c += loss_c; tot_s += loss_s; tot_e += loss_e; }   // the loss sums count every sample once
 #pragma unroll 1
         for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
             float z[16], gz[16], dz[16];
@@ -791,7 +802,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
         if (tid == 0) {
             tc05::fence_after_thread_sync();
             issue_linear_ts_backward(tmem_base + cZ2, tmem_base + cPhi, tmem_base + cPlo, wb_hi, wb_lo);   // dH1 over Z2
-            issue_weight_grad(tmem_base + cG2, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, 32);       // dW2[:, 0:32]
+            issue_weight_grad(tmem_base + cG2, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, 32, !first_tile);   // dW2[:, 0:32]
             tc05::mma_commit(bar);
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
@@ -814,7 +825,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
         __syncthreads();
         if (tid == 0) {
             tc05::fence_after_thread_sync();
-            issue_weight_grad(tmem_base + cG2 + 32, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, 32);
+            issue_weight_grad(tmem_base + cG2 + 32, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, 32, !first_tile);
             tc05::mma_commit(bar);
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
@@ -854,11 +865,12 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
         __syncthreads();
         if (tid == 0) {
             tc05::fence_after_thread_sync();
-            issue_weight_grad(tmem_base + cG1, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, N1);
+            issue_weight_grad(tmem_base + cG1, ga_addr, kGAPlaneBytes, gb_addr, kGroupPlaneBytes, N1, !first_tile);
             tc05::mma_commit(bar);
         }
         tc05::mbar_wait(bar, phase & 1); ++phase;
         tc05::fence_after_thread_sync();
+        }   // tiles of this CTA
 
         TC_MARK(8);
         // ------------------------------------------------------------ gradients -> flat buffer (rows j = 16 quarter + lane, lane < 16;
@@ -918,7 +930,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
 
         // ------------------------------------------------------------ loss sums
         {
-            float c = loss_c, s = loss_s, e = loss_e;
+            float c = tot_c, s = tot_s, e = tot_e;
             block_sum3<kNT>(c, s, e, red);
             if (tid == 0) {
                 if (sharded) { g[numel] = c * inv_bsz; g[numel + 1] = s * inv_bsz; g[numel + 2] = e * inv_bsz; }
@@ -1017,7 +1029,9 @@ int b200rl_launch_update_tc(const UpdateArgs& A_in, int tiles, cudaStream_t stre
     const int S = A.net[0].dims[0], OUT = A.net[0].dims[3];
     auto launch = [&](auto kern) -> int {
         B200RL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        kern<<<dim3((unsigned)tiles, 2), kNT, kSmemBytes, stream>>>(A);
+        // one CTA per SM and net at most (196 KB of shared memory each): a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+        const int ctas = tiles < kMaxCtasPerNet ? tiles : kMaxCtasPerNet;
+        kern<<<dim3((unsigned)ctas, 2), kNT, kSmemBytes, stream>>>(A);
         return 0;
     };
     int rc;

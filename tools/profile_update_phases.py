@@ -17,7 +17,7 @@ for _ in range(4):
     agent.update_net(list(agent.explore_env(env, H)))
 th.cuda.synchronize()
 marks = agent._workspace[64:64 + 11 * 8].view(th.int64).cpu().numpy()
-names = ["start", "stage params + gather", "x~ rows written", "L1 done", "H1 + L2 done", "head + loss", "dZ2 + dH1 + G2 pass 1", "G2 pass 2",
+names = ["start", "stage params + layer-1 planes", "gather + x~ rows written", "L1 done", "H1 + L2 done", "head + loss", "dZ2 + dH1 + G2 pass 1", "G2 pass 2",
          "dZ1 + G1", "gradients out + loss sums", "exchange + clip + Adam"]
 print("phase marks of the actor CTA, last minibatch; SM cycles:")
 for i in range(1, 11):
