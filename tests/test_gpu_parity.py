@@ -686,3 +686,26 @@ def test_large_minibatch_against_oracle(batch):
     for which, module, net in (("actor", agent.act, actor), ("critic", agent.cri, critic)):
         for a, b in zip(gu.flat_params(G.module_to_net(module)), gu.flat_params(net)):
             G.assert_close(a, b, RTOL, 2e-6, which)
+
+
+def test_net_descriptor_follows_parameter_storage():
+    """The cached C descriptor of a net is revalidated by the parameters' current addresses: an in-place change (what
+    ``load_state_dict`` and the engine's own Adam do) keeps it, re-pointing a parameter at new storage (``module.to()``,
+    ``p.data = ...``) rebuilds it -- the engine must never read a stale storage."""
+    g = gu.load("synth_s8_a2_64x64")
+    agent = G.agent_from_golden(g)
+    state = G.cuda(g["nets.state"])
+    v0 = agent.get_values(state).clone()
+    desc0 = agent._net_desc(agent.cri)
+    with th.no_grad():
+        agent.cri.net[0].weight.mul_(1.5)                      # in place: same storage, same descriptor
+    assert agent._net_desc(agent.cri) is desc0
+    with th.no_grad():
+        want = agent.cri(state).reshape(-1)
+    G.assert_close(agent.get_values(state), want.cpu().numpy(), RTOL, 2e-6)
+    assert not th.allclose(agent.get_values(state), v0)
+    agent.cri.net[2].bias.data = agent.cri.net[2].bias.data.clone() + 0.25   # new storage: descriptor rebuilt
+    assert agent._net_desc(agent.cri) is not desc0
+    with th.no_grad():
+        want = agent.cri(state).reshape(-1)
+    G.assert_close(agent.get_values(state), want.cpu().numpy(), RTOL, 2e-6)
