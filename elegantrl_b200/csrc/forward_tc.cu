@@ -126,8 +126,7 @@ mlp64_forward_tc_kernel(const __grid_constant__ b200rl_net net, const float* __r
             float z[16];
             tc05::tmem_ld_32x32b_x16(tl + cZ + 16 * c, z);
             tc05::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+            gelu_only16(z);
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, z);
         }
         tc05::tmem_st_wait();
@@ -150,7 +149,8 @@ mlp64_forward_tc_kernel(const __grid_constant__ b200rl_net net, const float* __r
             tc05::tmem_ld_32x32b_x16(tl + cZ + 16 * c, z);
             tc05::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j] + small[kSmB2 + 16 * c + j]);
+            for (int j = 0; j < 16; ++j) z[j] += small[kSmB2 + 16 * c + j];
+            gelu_only16(z);
 #pragma unroll
             for (int a = 0; a < OUTC; ++a) {
                 if (a < OUT) {

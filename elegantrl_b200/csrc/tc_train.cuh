@@ -62,6 +62,47 @@ DEV float gelu_only(float x) {
     p = fmaf(p, zn, 1.151116861e+00f);
     return fmaf(zn, tc05::ex2_approx(fmaf(p, zn, -1.0f)), fmaxf(x, 0.0f));
 }
+// The same two functions on PAIRS with the packed fp32 instructions of sm_100 (FFMA2 / FMUL2: one issue slot for two lanes'
+// worth of fma; every operation rounds exactly like its scalar counterpart above, so results are bit-identical): the GELUs
+// are most of this kernel's CUDA-core work AND of its code size (it is executed by a handful of warps, instruction fetch is
+// its second largest stall).
+DEV float2 splat2(float v) { return make_float2(v, v); }
+DEV float2 gelu_only2(float2 x) {
+    constexpr float L = 6.2225397f;
+    const float2 zn = make_float2(fmaxf(-fabsf(x.x), -L), fmaxf(-fabsf(x.y), -L));
+    float2 p = __ffma2_rn(splat2(1.775934289e-05f), zn, splat2(6.477866232e-04f));
+    p = __ffma2_rn(p, zn, splat2(7.724114180e-03f));
+    p = __ffma2_rn(p, zn, splat2(5.292681266e-02f));
+    p = __ffma2_rn(p, zn, splat2(-4.590827042e-01f));
+    p = __ffma2_rn(p, zn, splat2(1.151116861e+00f));
+    const float2 t = __ffma2_rn(p, zn, splat2(-1.0f));
+    const float2 q = make_float2(tc05::ex2_approx(t.x), tc05::ex2_approx(t.y));
+    return __ffma2_rn(zn, q, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+DEV void gelu_and_grad2(float2 x, float2& g, float2& dg) {
+    constexpr float L = 6.2225397f;
+    const float2 zn = make_float2(fmaxf(-fabsf(x.x), -L), fmaxf(-fabsf(x.y), -L));
+    float2 p = __ffma2_rn(splat2(1.775934289e-05f), zn, splat2(6.477866232e-04f));
+    p = __ffma2_rn(p, zn, splat2(7.724114180e-03f));
+    p = __ffma2_rn(p, zn, splat2(5.292681266e-02f));
+    p = __ffma2_rn(p, zn, splat2(-4.590827042e-01f));
+    p = __ffma2_rn(p, zn, splat2(1.151116861e+00f));
+    const float2 t = __ffma2_rn(p, zn, splat2(-1.0f));
+    const float2 q = make_float2(tc05::ex2_approx(t.x), tc05::ex2_approx(t.y));
+    g = __ffma2_rn(zn, q, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+    const float2 e = __fmul2_rn(__fmul2_rn(zn, zn), splat2(-0.72134752044f));
+    const float2 pdf = __fmul2_rn(make_float2(tc05::ex2_approx(e.x), tc05::ex2_approx(e.y)), splat2(kInvSqrt2Pi));
+    dg = __ffma2_rn(x, pdf, make_float2(x.x >= 0.0f ? 1.0f - q.x : q.x, x.y >= 0.0f ? 1.0f - q.y : q.y));
+}
+// 16 values in place
+DEV void gelu_only16(float (&z)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        const float2 g = gelu_only2(make_float2(z[j], z[j + 1]));
+        z[j] = g.x; z[j + 1] = g.y;
+    }
+}
+
 // Sum over the 32 lanes of a warp of 16 per-lane values with 16 shuffles (recursive halving: every step exchanges half of
 // the values a lane still holds): afterwards lane l holds the total of value index (l >> 1) & 15 (lanes l and l ^ 1 the same).
 DEV float warp_reduce16(float (&v)[16], int lane) {

@@ -604,8 +604,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
             float z[16];
             tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
             tc05::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+            gelu_only16(z);
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, z);
             if (c < 2) store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, row, 16 * c, z);
         }
@@ -632,7 +631,8 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
             tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
             tc05::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j] + small[kSmB2 + 16 * c + j]);
+            for (int j = 0; j < 16; ++j) z[j] += small[kSmB2 + 16 * c + j];
+            gelu_only16(z);
 #pragma unroll
             for (int a = 0; a < OUTC; ++a) {
                 if (a < OUT) {
@@ -767,13 +767,19 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
             tc05::tmem_ld_32x32b_x16(tl + cZ2 + 16 * c, z);
             tc05::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float dg;
-                gelu_and_grad(z[j] + small[kSmB2 + 16 * c + j], gz[j], dg);
-                float dh = 0.0f;
+            for (int j = 0; j < 16; j += 2) {
+                float2 g2, dg2;
+                gelu_and_grad2(make_float2(z[j] + small[kSmB2 + 16 * c + j], z[j + 1] + small[kSmB2 + 16 * c + j + 1]), g2, dg2);
+                gz[j] = g2.x; gz[j + 1] = g2.y;
+                float dh0 = 0.0f, dh1 = 0.0f;
 #pragma unroll
-                for (int a = 0; a < OUTC; ++a) if (a < OUT) dh = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j], dh);
-                dz[j] = dh * dg;
+                for (int a = 0; a < OUTC; ++a) {
+                    if (a < OUT) {
+                        dh0 = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j], dh0);
+                        dh1 = fmaf(dout[a], small[kSmW3 + a * kHid + 16 * c + j + 1], dh1);
+                    }
+                }
+                dz[j] = dh0 * dg2.x; dz[j + 1] = dh1 * dg2.y;
             }
             store_hi_lo_tmem(tl + cPhi + 16 * c, tl + cPlo + 16 * c, dz);
             store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, row, 16 * c, dz);
@@ -815,8 +821,7 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
                 float z[16];
                 tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
                 tc05::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) z[j] = gelu_only(z[j]);
+                gelu_only16(z);
                 store_hi_lo_rows(smem + kOffGB, smem + kOffGB + kGroupPlaneBytes, row, 16 * (c - 2), z);
             }
         }
@@ -840,10 +845,10 @@ __global__ void __launch_bounds__(kNT, 1) ppo_update_tc_kernel(const __grid_cons
             tc05::tmem_ld_32x32b_x16(tl + cZ1 + 16 * c, z);
             tc05::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float gj, dg;
-                gelu_and_grad(z[j], gj, dg);
-                dh[j] *= dg;
+            for (int j = 0; j < 16; j += 2) {
+                float2 g2, dg2;
+                gelu_and_grad2(make_float2(z[j], z[j + 1]), g2, dg2);
+                dh[j] *= dg2.x; dh[j + 1] *= dg2.y;
             }
             store_hi_lo_rows(smem + kOffGA, smem + kOffGA + kGAPlaneBytes, row, 16 * c, dh);
         }
