@@ -125,13 +125,12 @@ def cpu_backend():
     return "port", time_cpu_cycles, "oracle/cpu_port.py (oracle/_ref absent)"
 
 
-def calibrate_threads(time_fn, num_envs=NUM_ENVS):
+def calibrate_threads(time_fn, num_envs=NUM_ENVS, cache=os.path.join("/tmp", "b200rl_cpu_threads.json")):
     """torch's default of one intra-op thread per logical CPU is several times SLOWER than 8-32 threads on these tiny
     ops, so the baseline uses the best count -- chosen on FULL-SIZE cycles (the same workload that is then timed), best
     of 3 per candidate after one warm-up.  The choice is cached on the box (/tmp) for an hour: the driver runs the reference
     arm and the engine arm back to back, and both legs must time the CPU implementation with the SAME thread count (the
     host is shared and noisy: two independent calibrations picked 8 and 32 threads in one round-2 run)."""
-    cache = os.path.join("/tmp", "b200rl_cpu_threads.json")
     try:
         c = json.load(open(cache))
         if time.time() - c["when"] < 3600 and c["num_envs"] == num_envs and c["ncpu"] == (os.cpu_count() or 8):
