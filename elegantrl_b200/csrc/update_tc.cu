@@ -3,18 +3,24 @@
 // (reference AgentPPO.update_objectives, elegantrl/agents/AgentPPO.py:173-205; AgentBase.optimizer_backward,
 // elegantrl/agents/AgentBase.py:239-248); every other shape keeps the generic FP32-pipe kernels of update.cu.
 //
-// One CTA = one tile of 128 sampled transitions of ONE net (grid = tiles x 2); 256 threads: warps w and w + 4 share the TMEM
-// lane quarter w % 4 (sample = lane) and split the 64 feature columns, so two threads work on every sample.  Every dense
+// A CTA works on tiles of 128 sampled transitions of ONE net (grid = CTAs x 2 nets); 256 threads: warps w and w + 4 share the
+// TMEM lane quarter w % 4 (sample = lane) and split the 64 feature columns, so two threads work on every sample.  Every dense
 // contraction of the forward AND backward pass is a tcgen05 tile (3xTF32: hi / lo planes, fp32 accumulate in TMEM):
 //   L1   Z1 [128 x 64] = x~ B1^T            x~ = [x_hi, 1, x_lo, 0] (bias folded), K = round_up(2 S + 1, 8)      SS
 //   L2   Z2 [128 x 64] = H1 W2^T            H1 = GELU(Z1) as hi / lo planes in tensor memory (b2 added on read)   TS
 //   dH1  [128 x 64]    = dZ2 W2             dZ2 planes in tensor memory; W2's backward (MN-major) image          TS
 //   G2   [ 64 x 64]    = dZ2^T H1           = dW2, in two passes of 32 columns: contraction over the SAMPLES;
 //   G1   [ 64 x N1]    = dZ1^T [X  | 1]     = [dW1 | db1]  both operands are row-written MN-major images          SS
-// GELU / GELU', the head (64 -> OUT), the PPO loss and its derivative run on CUDA cores, thread = sample; the head's
-// weight gradient is reduced with shuffles.  Gradients go to the flat buffer of the workspace; clip + Adam is the shared
-// apply_net (update_common.cuh).  With one tile per net (batch_size <= 128: the Config default) the kernel is PERSISTENT:
-// all minibatches of update_net in one launch, two CTAs that never synchronise with each other.
+// GELU / GELU' (packed pairs), the head (64 -> OUT), the PPO loss and its derivative run on CUDA cores, thread = sample; the
+// head's weight gradient is reduced with shuffles.
+//   * batch_size <= 128 (the Config default): the launch is PERSISTENT -- all minibatches of update_net in one launch of two
+//     CTAs that never synchronise with each other; parameters and Adam moments stay resident in tensor memory between the
+//     minibatches (opt_load / opt_apply_resident), the gradient lives in shared memory, the operand images of minibatch u + 1
+//     are written from the registers of minibatch u's Adam step, and the sampled record of minibatch u + 1 is requested
+//     during the backward pass of minibatch u.  Env shards: the exchange with the peer GPUs happens in here too (px_*).
+//   * larger minibatches: one launch per minibatch, at most 74 CTAs per net, each walking several tiles with the weight-gradient
+//     UMMAs accumulating in tensor memory; one RED.ADD pass per CTA into the flat buffer, last CTA of a net applies clip + Adam
+//     (apply_net, update_common.cuh).
 #include <stdlib.h>
 #include <string.h>
 
