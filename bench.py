@@ -319,7 +319,9 @@ def run_engine(args):
                         "bytes_per_env_step": HBM_BYTES_PER_ENV_STEP}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world, n_envs), sharded_mode=(getattr(agent, "sharded_mode", None) if world > 1 else None)), "clocks": clocks,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world, n_envs),
+            # how the env shards exchange what the update needs (outside `config`: both arms describe the same workload)
+            "exchange": (getattr(agent, "sharded_mode", None) if world > 1 else None), "clocks": clocks,
             "e2e": {"value": env_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 3 * n_envs * 4, "d2h_bytes_per_step": 3 * 4 + n_envs * 3 * 4 + 3 * n_envs * 4,
                     "ms_per_step": e2e_ms / args.steps},

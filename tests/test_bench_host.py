@@ -45,3 +45,12 @@ def test_workload_config_names_the_baseline_configuration():
     assert "65 536" in cfg["workload"] and cfg["num_envs_total"] == bench.NUM_ENVS
     cfg8 = bench.workload_config(8, 8192)
     assert cfg8["num_envs_per_gpu"] == 8192 and cfg8["num_envs_total"] == 65536 and cfg8["parallelism"] == "env-shard x8"
+
+
+def test_both_arms_describe_the_same_workload():
+    """The reference arm builds its ``config`` from ``workload_config(gpus)``, the engine arm from ``workload_config(world,
+    envs_per_gpu)``: for the default (weak-scaling) run they must be the same dict, key for key (the driver compares them)."""
+    for n in (1, 2, 4, 8):
+        assert bench.workload_config(n) == bench.workload_config(n, bench.NUM_ENVS)
+    src = open(bench.__file__).read()
+    assert '"config": workload_config(args.gpus)' in src and '"config": workload_config(world, n_envs)' in src
